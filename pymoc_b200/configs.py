@@ -1,0 +1,252 @@
+"""The reference's example scripts as ensemble builders (BASELINE.json ``configs``).
+
+Each function returns a :class:`~pymoc_b200.spec.ModelSpec` whose member 0 (or the
+member at the script's own parameter values) reproduces the set-up lines of the cited
+script verbatim -- same grids, same initial profiles, same constants -- and whose other
+members sweep the axes SURVEY.md section 8d names.  Sweeps are deterministic tensor-product
+lattices (the reference has no RNG).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .spec import (ChannelSpec, ColumnSpec, MixedLayerSpec, ModelSpec, ThermwindSpec)
+
+DAY = 86400
+
+
+def lattice(**axes):
+  """Tensor-product lattice: dict of equally long flat arrays, last axis fastest."""
+  names = list(axes)
+  grids = np.meshgrid(*[np.asarray(axes[n], dtype=np.float64) for n in names], indexing='ij')
+  return {n: np.ascontiguousarray(g.ravel()) for n, g in zip(names, grids)}
+
+
+def _sizes(M, naxes):
+  """Split M (a power of two) into ``naxes`` near-equal power-of-two factors."""
+  e = int(round(np.log2(M)))
+  if 2**e != M:
+    raise ValueError('ensemble size must be a power of two, got %d' % M)
+  base, extra = divmod(e, naxes)
+  return [2**(base + (1 if i < extra else 0)) for i in range(naxes)]
+
+
+# ----------------------------------------------------------------------------- C1
+def c1_timestepping(M=1, nz=70):
+  """examples/example_timestepping.py:17-80 -- Column + Psi_Thermwind(b2=0.), K=1."""
+  bs, bbot, A = 0.03, -0.0004, 8e13
+  z = np.asarray(np.linspace(-3500, 0, nz))
+  kap = lambda zz: 1e-5 + 3e-5 * np.exp(zz / 100) + 3e-4 * np.exp(-zz / 1000 - 4)
+  b0 = bs * np.exp(z / 300.) + bbot
+  if M == 1:
+    kappa, sweep = kap(z), {}
+  else:  # scale the diffusivity profile
+    sweep = lattice(kapfac=np.linspace(0.5, 2.0, M))
+    kappa = sweep['kapfac'][:, None] * kap(z)[None, :]
+  return ModelSpec(
+      M=M, z=z, dt=60 * DAY, K=1, name='C1 example_timestepping', sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A, bs, b0, bbot=bbot),
+      tw=ThermwindSpec.build(z, f=1.2e-4, b2=0. + 0 * z), order='post', iso=False)
+
+
+# ----------------------------------------------------------------------------- C2
+def c2_column_so(M=65536, nz=200, ny=40, dt_days=10., ntau=None):
+  """Single column + explicit Psi_SO.
+
+  examples/example_twocol_plusSO.py:18-115 with the north column and the thermal-wind
+  closure removed, ``wA = -SO.Psi*1e6``, ``c=None``; tau x kappa lattice.
+  """
+  bs, bmin, l = 0.03, 0.0, 2.e6
+  y = np.asarray(np.linspace(0, l, ny))
+  bs_SO = (bs - bmin) * (y / y[-1])**2 + bmin
+  z = np.asarray(np.linspace(-4000, 0, nz))
+  if ntau is None:
+    ntau = _sizes(M, 2)[0]
+  nkap = M // ntau
+  sweep = lattice(tau=np.linspace(0.05, 0.25, ntau) if ntau > 1 else [0.13],
+                  kappa=np.geomspace(1e-5, 1e-4, nkap) if nkap > 1 else [2e-5])
+  dt = dt_days * DAY
+  K = int(np.floor(2. * 360 * 86400 / dt))
+  kappa = sweep['kappa'][:, None] + 0 * z[None, :]
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, name='C2 column+SO', sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, 6e13, bs, bs * np.exp(z / 300.), bbot=bmin),
+      so=ChannelSpec.build(y, bs_SO, sweep['tau'], f=1e-4, L=5e6, KGM=1000.), order='post')
+
+
+# ------------------------------------------------------------------------- twocol
+def twocol(M=1):
+  """examples/example_twocol.py:17-96 -- two columns + isopycnal thermal wind, no SO."""
+  bs, bs_north, bbot, A = 0.03, 0.0, -0.003, 8e13
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  dt = 86400 * 30
+  K = int(np.floor(2 * 360 * 86400 / dt))
+  kap = 1e-5 + 3e-4 * np.exp(-z / 1000 - 4)
+  sweep = lattice(kapfac=np.linspace(0.5, 2.0, M)) if M > 1 else {}
+  kappa = kap if M == 1 else sweep['kapfac'][:, None] * kap[None, :]
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, name='example_twocol', sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A, bs, bs * np.exp(z / 300.), bbot=bbot),
+      north=ColumnSpec.build(z, kappa, A / 100., bs_north, 1e-3 * bs * np.exp(z / 300.), bbot=bbot,
+                             do_conv=True),
+      tw=ThermwindSpec.build(z, f=1.2e-4), order='post', iso=True)
+
+
+# ----------------------------------------------------------------------------- C3
+def c3_twocol_so(M=262144, c=None, axes=None):
+  """examples/example_twocol_plusSO.py:18-115 -- two columns + thermal wind + Psi_SO.
+
+  ``c=0.1`` gives the literal script (F2010 BVP smoother, ``bvp_with_Ek=True``);
+  ``c=None`` its explicit-GM twin.  Lattice: tau x kappa x
+  bs_north x A_basin (64 x 64 x 8 x 8 at the BASELINE size).
+  """
+  bs, bmin, l = 0.03, 0.0, 2.e6
+  y = np.asarray(np.linspace(0, l, 40))
+  bs_SO = (bs - bmin) * (y / y[-1])**2 + bmin
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  dt = 86400 * 30
+  K = int(np.floor(2. * 360 * 86400 / dt))
+  if M == 1:
+    sweep = lattice(tau=[0.13], kappa=[2e-5], bs_north=[0.004], A_basin=[6e13])
+  else:
+    if axes is None:
+      e = int(round(np.log2(M)))
+      small = min(3, e // 4)
+      big = e - 2 * small
+      axes = (2**(big - big // 2), 2**(big // 2), 2**small, 2**small)
+    nt, nk, nn, na = axes
+    sweep = lattice(tau=np.linspace(0.05, 0.25, nt) if nt > 1 else [0.13],
+                    kappa=np.geomspace(1e-5, 1e-4, nk) if nk > 1 else [2e-5],
+                    bs_north=np.linspace(0.002, 0.006, nn) if nn > 1 else [0.004],
+                    A_basin=np.linspace(4e13, 8e13, na) if na > 1 else [6e13])
+  assert sweep['tau'].size == M, (sweep['tau'].size, M)
+  kappa = sweep['kappa'][:, None] + 0 * z[None, :]
+  A_b = sweep['A_basin'][:, None] + 0 * z[None, :]
+  e300 = np.exp(z / 300.)
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, name='C3 example_twocol_plusSO' + ('' if c is None else ' c=%g' % c), sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A_b, bs, bs * e300, bbot=bmin),
+      north=ColumnSpec.build(z, kappa, A_b / 50., sweep['bs_north'], sweep['bs_north'][:, None] * e300[None, :],
+                             bbot=bmin, do_conv=True),
+      tw=ThermwindSpec.build(z, f=1e-4),
+      so=ChannelSpec.build(y, bs_SO, sweep['tau'], f=1e-4, L=5e6, KGM=1000., c=c, bvp_with_Ek=c is not None),
+      order='post', iso=True)
+
+
+# ------------------------------------------------------------------------ C4 / C5
+_KAPGCM = np.array([
+    1.2e-4, 0.882e-4, 0.544e-4, 0.393e-4, 0.305e-4, 0.235e-4, 0.207e-4, 0.210e-4, 0.213e-4, 0.216e-4,
+    0.220e-4, 0.226e-4, 0.247e-4, 0.316e-4, 0.377e-4, 0.407e-4, 0.389e-4, 0.407e-4, 0.454e-4, 0.517e-4,
+    0.633e-4, 0.757e-4, 0.899e-4, 1.056e-4, 1.246e-4, 1.584e-4, 1.884e-4, 2.053e-4, 2.168e-4, 2.332e-4
+])
+_ZGCM = -1e3 * np.array([
+    0.0, 0.0200, 0.045, 0.075, 0.110, 0.150, 0.200, 0.260, 0.330, 0.410, 0.500, 0.600, 0.720, 0.860, 1.020,
+    1.200, 1.400, 1.600, 1.800, 2.000, 2.200, 2.400, 2.600, 2.800, 3.000, 3.200, 3.400, 3.600, 3.800, 4.000
+])
+
+
+def _channel_surface(y, l, bs, bminSO, Bloss):
+  """Restoring target, flux and mask of run_JansenNadeau_2018.py:72-83 (per member)."""
+  bs = np.atleast_1d(bs)[:, None]
+  bmin = np.atleast_1d(bminSO)[:, None]
+  n = max(bs.shape[0], bmin.shape[0])
+  eq = np.broadcast_to(0. * y[None, :] + bmin, (n, y.size)).copy()
+  alpha = (1. - np.cos(np.pi * (l - y[5]) / 7.4e6))
+  eq[:, 6:] = (bs - bmin) * (1. - np.cos(np.pi * (y[6:] - y[5]) / 7.4e6))[None, :] / alpha + bmin
+  surflux = np.zeros((np.atleast_1d(Bloss).size, y.size))
+  surflux[:, 1:6] = -np.atleast_1d(Bloss)[:, None]
+  rest_mask = 0. * y
+  rest_mask[6:-1] = 1.
+  return eq, surflux, rest_mask
+
+
+def c4_jansen_nadeau(M=1, axes=None):
+  """examples/run_JansenNadeau_2018.py:33-261 (default flags) -- two convecting columns,
+  thermal wind with isopycnal remap, explicit Psi_SO, SO_ML, bottom-boundary switches.
+
+  Lattice: tau x kapfac x db x B x KGM.
+  """
+  if M == 1:
+    sweep = lattice(tau=[0.12], kapfac=[1.0], db=[0.0], B=[5.9e3], KGM=[800.])
+  else:
+    n = axes if axes is not None else _sizes(M, 5)
+    sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
+                    kapfac=np.geomspace(0.5, 2., n[1]) if n[1] > 1 else [1.0],
+                    db=np.linspace(-0.004, 0.004, n[2]) if n[2] > 1 else [0.0],
+                    B=np.linspace(3e3, 9e3, n[3]) if n[3] > 1 else [5.9e3],
+                    KGM=np.linspace(500., 1500., n[4]) if n[4] > 1 else [800.])
+  assert sweep['tau'].size == M
+  db = sweep['db']
+  bs, bs_north, bminSO = 0.02 + db, -0.001 + db, 0.0 + db
+  h, L = 50., 4e6
+  Bloss = sweep['B'] / L / 2e5
+  l = 2.e6
+  y = np.asarray(np.linspace(0, l, 51))
+  bs_SO_eq, surflux, rest_mask = _channel_surface(y, l, bs, bminSO, Bloss)
+  A_basin = 8e13
+  dt = 86400. * 30
+  K = int(np.floor(1. * 360. * 86400. / dt))
+  z = np.asarray(np.linspace(-4000., 0., 81))
+  kfull = np.interp(-z, -_ZGCM, _KAPGCM)
+  keff = np.interp(-z, -_ZGCM, _KAPGCM) * (1. - np.maximum(-4000. - z + 500., 0.) / 500.)**2
+  kappa = sweep['kapfac'][:, None, None] * np.stack([kfull, keff])[None, :, :]
+  b_basin = bs[:, None] * np.exp(z / 300.)[None, :] + bs_north[:, None] * (z / z[0])[None, :]
+  b_north = bs_north[:, None] * ((z / z[0])**2.)[None, :]
+  bs_SO = bs_SO_eq.copy()
+  # Psi_SO is first diagnosed inside the loop (ii=0) *after* line 156 set bs_SO[-1]=bs
+  bs_SO[:, -1] = bs
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, nb=500, name='C4 run_JansenNadeau_2018', sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A_basin, bs, b_basin, bbot=b_basin[:, 0], do_conv=True, var0=1),
+      north=ColumnSpec.build(z, kappa, A_basin / 50., bs_north, b_north, bbot=b_north[:, 0], do_conv=True,
+                             var0=1),
+      tw=ThermwindSpec.build(z, f=1.2e-4),
+      so=ChannelSpec.build(y, bs_SO, sweep['tau'], f=1.2e-4, L=L, KGM=sweep['KGM']),
+      ml=MixedLayerSpec.build(y, bs_SO, Ks=400., h=h, L=L, surflux=surflux, rest_mask=rest_mask,
+                              b_rest=bs_SO_eq, v_pist=1.5 / 86400.),
+      order='jn', iso=True)
+
+
+def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None):
+  """examples/run_single_global_basin.py:40-229 with ``z=linspace(-4500,0,nz)``.
+
+  Lattice: tau x kapfac x KGM x Ks.  The explicit diffusion
+  needs dt <= dz^2/(2 kappa_max): 30 d at nz=46, 5 d at nz=200, 0.01 d at nz=4096 (H6).
+  """
+  if M == 1:
+    sweep = lattice(tau=[0.12], kapfac=[1.0], KGM=[1.0e3], Ks=[1.0e3])
+  else:
+    n = axes if axes is not None else _sizes(M, 4)
+    sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
+                    kapfac=np.geomspace(0.5, 2., n[1]) if n[1] > 1 else [1.0],
+                    KGM=np.linspace(500., 1500., n[2]) if n[2] > 1 else [1.0e3],
+                    Ks=np.linspace(500., 1500., n[3]) if n[3] > 1 else [1.0e3])
+  assert sweep['tau'].size == M
+  bs, bs_north, bminSO = 0.025, 0.0, 0.0
+  h, L = 50., 2e7
+  Bloss = 5.0e4 / L / 2e5
+  l = 2.e6
+  y = np.asarray(np.linspace(0, l, 51))
+  bs_SO_eq, surflux, rest_mask = _channel_surface(y, l, np.array([bs]), np.array([bminSO]), np.array([Bloss]))
+  A_basin = 3.2e14
+  dt = 86400. * dt_days
+  K = int(np.floor(2. * 360. * 86400. / dt))
+  z = np.asarray(np.linspace(-4500., 0., nz))
+  kf = sweep['kapfac'][:, None]
+  kfull = kf * 9e-6 * np.exp(-z / 1200)[None, :] + 7e-5 * np.exp(z / 50)[None, :]
+  keff = kfull * ((1. - np.maximum(-4500. - z + 500., 0.) / 500.)**2)[None, :]
+  kappa = np.stack([kfull, keff], axis=1)
+  b_basin = bs * np.exp(z / 400.) - 0.0001 * z / z[0]
+  b_north = bs_north - 0.0001 * (z / z[0])**2.
+  bs_SO = bs_SO_eq.copy()
+  bs_SO[:, :6] = -0.0001
+  bs_SO[:, -1] = bs
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, nb=500, name='C5 run_single_global_basin nz=%d' % nz, sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A_basin, bs, b_basin, bbot=b_basin[0], do_conv=True, var0=1),
+      north=ColumnSpec.build(z, kappa, A_basin / 100., bs_north, b_north, bbot=b_north[0], do_conv=True, var0=1),
+      tw=ThermwindSpec.build(z, f=1.2e-4),
+      so=ChannelSpec.build(y, bs_SO, sweep['tau'], f=1.2e-4, L=L, KGM=sweep['KGM']),
+      ml=MixedLayerSpec.build(y, bs_SO, Ks=sweep['Ks'], h=h, L=L, surflux=surflux, rest_mask=rest_mask,
+                              b_rest=bs_SO_eq, v_pist=1.5 / 86400.),
+      order='jn', iso=True)
