@@ -1,0 +1,176 @@
+/* pymoc_b200 -- C ABI of the B200-native PyMOC time-stepping engine.
+ *
+ * The reference (pymoc 0.0.1rc5) has no FFI: its boundary is the Python class surface
+ * Column / Psi_Thermwind / Psi_SO / SO_ML plus the hand-written loops in examples/
+ * (SURVEY.md section 8b).  Every entry point below names the reference interface it
+ * replaces (path:line under /root/reference).  INTEGRATION.md shows the ctypes stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; all floating point is IEEE binary64;
+ *  - every pointer is a DEVICE pointer unless the function name ends in _host;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); device
+ *    entry points are asynchronous on it and allocate nothing;
+ *  - every function returns a pmoc_status (0 = ok); no exception crosses the boundary;
+ *  - batched over `M` independent ensemble members; a `pmoc_vec` whose `mstride` is 0 is
+ *    shared by all members, otherwise member m starts at ptr + m*mstride (in doubles);
+ *  - vertical arrays run bottom (z[0] = -H) to surface (z[nz-1] = 0) like the reference.
+ */
+#ifndef PYMOC_B200_H_
+#define PYMOC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMOC_ABI_VERSION 1
+#define PMOC_MAX_NZ_WARP 256 /* one warp per member up to this many levels */
+
+typedef enum {
+  PMOC_OK = 0,
+  PMOC_EINVAL = 1,       /* bad sizes / null pointers / inconsistent flags */
+  PMOC_EUNSUPPORTED = 2, /* valid request this build has no kernel for */
+  PMOC_ECUDA = 3,        /* a CUDA runtime call failed; see pmoc_last_error() */
+  PMOC_ENODEVICE = 4     /* no CUDA device: there is no CPU fallback */
+} pmoc_status;
+
+typedef struct {
+  const double* ptr;
+  int64_t mstride; /* doubles between consecutive members; 0 = shared */
+} pmoc_vec;
+
+/* per-member status bits written by the model kernels (pmoc_model.status) */
+#define PMOC_ST_NAN 1u            /* non-finite buoyancy at the end of the launch */
+#define PMOC_ST_BS_NONMONOTONE 2u /* bs(y) not monotone north of argmin: Brent path taken */
+#define PMOC_ST_BRENT_SIGN 4u     /* f(a), f(b) same sign: scipy.optimize.brentq would raise ValueError */
+#define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML */
+
+/* ---- one advective-diffusive column: reference class Column, column.py:19-72 ------------ */
+typedef struct {
+  double* b;      /* [M, nz] buoyancy, updated in place (column.py:249,268,271) */
+  pmoc_vec kappa; /* [nvar, nz] diffusivity sampled on z (make_func, column.py:58)       */
+  pmoc_vec dAk;   /* [nvar, nz] np.gradient(Area*kappa, z), host-evaluated (column.py:122) */
+  pmoc_vec Area;  /* [nz] */
+  pmoc_vec bs;    /* scalar: surface buoyancy (column.py:61) */
+  pmoc_vec N2min; /* scalar (column.py:65) */
+  pmoc_vec bzbot; /* scalar or ptr==NULL -> use bbot (column.py:232-233) */
+  double* bbot;   /* [M] bottom buoyancy; the 'jn' loop rewrites it every step */
+  int32_t* var;   /* [M] kappa variant in use (0..nvar-1); NULL when nvar == 1 */
+  int32_t nvar;
+  int32_t do_conv; /* timestep(..., do_conv=True) (column.py:336-341) */
+} pmoc_column;
+
+/* ---- coupled model = what an examples/ script wires together -------------------------- */
+#define PMOC_HAS_NORTH 1u /* second (northern) column, convecting as flagged              */
+#define PMOC_HAS_TW 2u    /* Psi_Thermwind between basin and north / fixed b2             */
+#define PMOC_ISO 4u       /* force columns with Psibz() instead of Psi (psi_thermwind.py:187-208) */
+#define PMOC_HAS_SO 8u    /* Psi_SO on the basin column                                   */
+#define PMOC_HAS_ML 16u   /* SO_ML mixed layer                                            */
+#define PMOC_ORDER_JN 32u /* loop order + bottom-boundary switches of
+                             examples/run_JansenNadeau_2018.py:201-261; otherwise the order of
+                             examples/example_twocol_plusSO.py:99-115 */
+
+typedef struct {
+  int64_t M;
+  int32_t nz, ny, nb; /* nb: isopycnal classes of Psib (psi_thermwind.py:137, default 500) */
+  int32_t K;          /* MOC_up_iters */
+  uint32_t flags;
+  double dt;
+  const double* z; /* [nz] shared grid */
+  const double* y; /* [ny] shared channel grid (NULL without SO) */
+
+  pmoc_column basin, north;
+
+  /* Psi_Thermwind (psi_thermwind.py:30-70) */
+  pmoc_vec tw_f;  /* scalar */
+  pmoc_vec tw_b2; /* [nz] fixed northern profile when there is no north column */
+
+  /* Psi_SO (psi_SO.py:17-104) */
+  pmoc_vec so_bs;  /* [ny] surface buoyancy (ignored with PMOC_HAS_ML: the mixed layer's bs is used,
+                      run_JansenNadeau_2018.py:214) */
+  pmoc_vec so_tau; /* scalar wind stress, or [ny] when so_tau_on_y != 0 */
+  pmoc_vec so_f, so_rho, so_L, so_KGM, so_smax;
+  pmoc_vec so_c; /* scalar F2010 phase speed; ptr==NULL -> explicit GM (psi_SO.py:325-327) */
+  int32_t so_tau_on_y;
+  int32_t so_bvp_with_Ek;
+  /* host-evaluated tapers (psi_SO.py:164-216); all-ones when the height is None, the Ekman
+     taper with HEk=None has its last element 0 (psi_SO.py:213-216) */
+  const double *so_sill_taper, *so_ek_taper, *so_top_taper, *so_bot_taper; /* [nz] shared */
+
+  /* SO_ML (SO_ML.py:17-71) */
+  double* ml_bs; /* [M, ny] state */
+  pmoc_vec ml_Ks, ml_h, ml_L, ml_vpist;
+  pmoc_vec ml_surflux, ml_rest_mask, ml_b_rest; /* [ny] */
+
+  /* diagnostics, all optional (NULL = not wanted) except those the loop carries between
+     launches: Psi_iso_b/Psi_iso_n (or Psi_tw without PMOC_ISO) and Psi_so */
+  double *Psi_tw, *Psi_iso_b, *Psi_iso_n; /* [M, nz] Sv */
+  double *psib, *bgrid;                   /* [M, nb]     */
+  double *Psi_so, *Psi_Ek, *Psi_GM;       /* [M, nz] Sv */
+  double* ml_Psi_s;                       /* [M, ny] Sv */
+  uint32_t* status;                       /* [M] PMOC_ST_* bits, OR-ed */
+} pmoc_model;
+
+/* library / device ----------------------------------------------------------------------- */
+int pmoc_abi_version(void);
+const char* pmoc_last_error(void);     /* text of the last PMOC_ECUDA on this thread */
+int pmoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Diagnose all streamfunctions of the model from its current state -- what the scripts do
+ * before their loop (examples/example_twocol_plusSO.py:61-80: AMOC.solve(); AMOC.Psibz();
+ * SO.solve()).  Needed once before the first pmoc_model_run of an order-'post' model. */
+int pmoc_model_diagnose(const pmoc_model* m, void* stream);
+
+/* Advance every member by `nsteps` iterations of the script loop, iteration counter starting
+ * at `it0` (streamfunctions are re-diagnosed on iterations with it % K == 0).  One fused
+ * kernel: state stays on-chip for all `nsteps`.  Replaces the loop bodies
+ * examples/example_timestepping.py:73-80, example_twocol.py:85-96,
+ * example_twocol_plusSO.py:99-115, run_JansenNadeau_2018.py:201-261,
+ * run_single_global_basin.py:172-229. */
+int pmoc_model_run(const pmoc_model* m, int64_t it0, int64_t nsteps, void* stream);
+
+/* Same as diagnose (when it0 == 0) + run, but every pointer in `m` is a HOST pointer: device
+ * buffers are allocated, inputs copied in, the fused kernel run, and state + diagnostics
+ * copied back before returning (synchronous).  This is the call a non-torch consumer binds. */
+int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nsteps);
+
+/* ---- per-module entry points (the reference's method surface), batched over M ----------- */
+
+/* Column.timestep (column.py:315-348).  `stages` selects what runs, in the reference's
+ * order: convect -> vertadvdiff -> horadv; vertadvdiff applies the surface condition
+ * b[-1]=bs unless do_conv (column.py:230-231). */
+#define PMOC_STAGE_CONVECT 1u
+#define PMOC_STAGE_VERTADVDIFF 2u
+#define PMOC_STAGE_HORADV 4u
+int pmoc_column_timestep(int64_t M, int32_t nz, const double* z, const pmoc_column* col, pmoc_vec wA,
+                         pmoc_vec vdx_in, pmoc_vec b_in, double dt, uint32_t stages, void* stream);
+
+/* Psi_Thermwind.solve (psi_thermwind.py:125-135): exact double quadrature of the linear BVP.
+ * gmid: optional [nz-1] samples of (b2-b1) at the cell mid-points for callable profiles
+ * (ptr==NULL -> piecewise-linear b's).  Psi in Sv. */
+int pmoc_thermwind_solve(int64_t M, int32_t nz, const double* z, pmoc_vec b1, pmoc_vec b2, pmoc_vec f,
+                         pmoc_vec gmid, double* Psi, void* stream);
+
+/* Psi_Thermwind.Psib / Psibz (psi_thermwind.py:137-208).  Outputs optional except psib. */
+int pmoc_thermwind_psib(int64_t M, int32_t nz, int32_t nb, pmoc_vec Psi, pmoc_vec b1, pmoc_vec b2,
+                        double* psib, double* bgrid, double* iso_b, double* iso_n, void* stream);
+
+/* Psi_SO.solve (psi_SO.py:333-354) with ys/calc_Ekman/calc_GM inside.  `so` reuses the
+ * Psi_SO fields of pmoc_model (so_*, y, ny, z, nz, M); b is the basin profile. */
+int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, double* Psi_Ek, double* Psi_GM,
+                  double* ys, uint32_t* status, void* stream);
+
+/* SO_ML.timestep / advdiff (SO_ML.py:198-303).  `ml` reuses the ml_* fields of pmoc_model. */
+int pmoc_ml_timestep(const pmoc_model* ml, pmoc_vec b_basin, pmoc_vec Psi_b, double dt, uint32_t* status,
+                     void* stream);
+
+/* FP64 roofline probe: a dependent-free DFMA stream on every SM; returns the measured
+ * TFLOP/s (2 flops per FMA) in *tflops.  Used by bench.py for the roofline denominator. */
+int pmoc_fp64_peak(double* tflops, double* sm_mhz_est, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYMOC_B200_H_ */

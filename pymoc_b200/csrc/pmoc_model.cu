@@ -1,0 +1,176 @@
+// The fused multi-step engine, instantiated for one levels-per-lane value per translation
+// unit (compile with -DPM_LPL=<2..8>).
+#include "pmoc_common.cuh"
+
+#ifndef PM_LPL
+#error "compile with -DPM_LPL=<levels per lane>"
+#endif
+
+namespace pmk {
+template <int LPL, unsigned TOPO>
+PM_GLOBAL void k_model(RunArgs a) {
+  constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
+  constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
+  const pmoc_model& M = a.m;
+  const SmemPlan& sp = a.sp;
+  const int nz = M.nz, ny = M.ny, nb = M.nb;
+  const int L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
+  double* sm = rt::smem();
+  double* zs = sm + sp.off_z;
+  double* ysm = sm + sp.off_y;
+  double* ws = sm + sp.off_warp0 + (size_t)sp.per_warp * W;
+  for (int i = W * 32 + L; i < sp.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
+  if (SO)
+    for (int i = W * 32 + L; i < sp.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
+  rt::syncblock();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= M.M) return;
+
+  ColRegs<LPL> cb, cn;
+  col_load<LPL>(cb, M.basin, m, nz);
+  if (NORTH) col_load<LPL>(cn, M.north, m, nz);
+  double b2fix[LPL];
+  if (TW && !NORTH) pm::load_lev<LPL>(b2fix, vrow(M.tw_b2, m), nz, 0.0);
+  const double tw_f = TW ? vat(M.tw_f, m) : 1.0;
+  pm::SoPar so{};
+  if (SO) {
+    so.tau_ave = pm::mean100(vat(M.so_tau, m));
+    so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
+    so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
+    so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
+    const double* src = vrow(M.so_bs, m);
+    for (int i = L; i < sp.nyp; i += 32) ws[sp.w_bs + i] = src[i < ny ? i : ny - 1];
+    rt::syncwarp();
+  }
+  unsigned status = 0;
+  const double dt = M.dt;
+
+  // Diagnose the streamfunctions from the current state and fold them into the stencils.
+  auto refresh = [&](bool write) {
+    double psi_tw[LPL], iso_b[LPL], iso_n[LPL], psi_so[LPL], wA[LPL];
+    if (TW) {
+      const double(&b2)[LPL] = NORTH ? cn.b : b2fix;
+      pm::tw_solve<LPL>(psi_tw, cb.b, b2, tw_f, zs, nz, nullptr);
+      if (write && M.Psi_tw) pm::store_lev<LPL>(psi_tw, M.Psi_tw + m * nz, nz);
+      if (ISO) {
+        double* psib_s = ws + sp.w_psib;
+        const pm::BGrid G = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_ctop, ws + sp.w_crinv,
+                                             ws + sp.w_cu, psib_s);
+        PM_UNROLL
+        for (int j = 0; j < LPL; ++j) {
+          const bool ok = pm::lev<LPL>(j) < nz;
+          iso_b[j] = ok ? pm::interp_bgrid(cb.b[j], G, psib_s) : 0.0;
+          iso_n[j] = ok ? pm::interp_bgrid(b2[j], G, psib_s) : 0.0;
+        }
+        if (write) {
+          pm::store_lev<LPL>(iso_b, M.Psi_iso_b + m * nz, nz);
+          pm::store_lev<LPL>(iso_n, M.Psi_iso_n + m * nz, nz);
+          if (M.psib)
+            for (int i = L; i < nb; i += 32) M.psib[m * nb + i] = psib_s[i];
+          if (M.bgrid)
+            for (int i = L; i < nb; i += 32) M.bgrid[m * nb + i] = G.at(i);
+        }
+        rt::syncwarp();
+      }
+    }
+    if (SO) {
+      double ek[LPL], gm[LPL], ysv[LPL];
+      pm::so_solve<LPL>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ny, so, zs, nz, &status);
+      if (write) {
+        pm::store_lev<LPL>(psi_so, M.Psi_so + m * nz, nz);
+        if (M.Psi_Ek) pm::store_lev<LPL>(ek, M.Psi_Ek + m * nz, nz);
+        if (M.Psi_GM) pm::store_lev<LPL>(gm, M.Psi_GM + m * nz, nz);
+      }
+    }
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const double north_leg = TW ? (ISO ? iso_b[j] : psi_tw[j]) : 0.0;
+      const double south_leg = SO ? psi_so[j] : 0.0;
+      wA[j] = (north_leg - south_leg) * 1e6;
+    }
+    col_refold<LPL>(cb, M.basin, m, wA, zs, nz, dt);
+    if (NORTH) {
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = -iso_n[j] * 1e6;
+      col_refold<LPL>(cn, M.north, m, wA, zs, nz, dt);
+    }
+  };
+
+  if (a.diagnose_only) {
+    refresh(true);
+    if (M.status && L == 0) M.status[m] |= status;
+    return;
+  }
+
+  // carried streamfunctions -> stencils (the loop uses the previous diagnosis until it % K == 0)
+  {
+    double wA[LPL], t1[LPL], t2[LPL];
+    if (TW) pm::load_lev<LPL>(t1, (ISO ? M.Psi_iso_b : M.Psi_tw) + m * nz, nz, 0.0);
+    if (SO) pm::load_lev<LPL>(t2, M.Psi_so + m * nz, nz, 0.0);
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? t1[j] : 0.0) - (SO ? t2[j] : 0.0)) * 1e6;
+    col_refold<LPL>(cb, M.basin, m, wA, zs, nz, dt);
+    if (NORTH) {
+      pm::load_lev<LPL>(t1, M.Psi_iso_n + m * nz, nz, 0.0);
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = -t1[j] * 1e6;
+      col_refold<LPL>(cn, M.north, m, wA, zs, nz, dt);
+    }
+  }
+  // surface condition of non-convecting columns (column.py:230-231); p = q = 0 keeps it
+  if (!cb.conv) pm::set_level<LPL>(cb.b, nz - 1, cb.bs);
+  if (NORTH && !cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
+
+  const long long K = M.K, it_end = a.it0 + a.nsteps;
+  // last iteration of this launch that re-diagnoses: only that one writes diagnostics to HBM
+  const long long last_refresh = ((it_end - 1) / K) * K;
+  long long ii = a.it0;
+  while (ii < it_end) {
+    // iterations up to and including the next multiple of K
+    long long stop = ((ii + K - 1) / K) * K;  // next ii' >= ii with ii' % K == 0
+    const bool hits = stop < it_end;
+    const long long upto = hits ? stop + 1 : it_end;
+    for (; ii < upto; ++ii) {
+      col_advance<LPL>(cb, zs, nz);
+      if (NORTH) col_advance<LPL>(cn, zs, nz);
+    }
+    if (hits) refresh(stop == last_refresh);
+  }
+
+  pm::store_lev<LPL>(cb.b, M.basin.b + m * nz, nz);
+  if (NORTH) pm::store_lev<LPL>(cn.b, M.north.b + m * nz, nz);
+  bool bad = false;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    if (pm::lev<LPL>(j) < nz) {
+      bad |= !(fabs(cb.b[j]) <= 1.79e308);
+      if (NORTH) bad |= !(fabs(cn.b[j]) <= 1.79e308);
+    }
+  }
+  if (rt::ballot(bad)) status |= PMOC_ST_NAN;
+  if (M.status && L == 0) M.status[m] |= status;
+}
+
+template <int LPL>
+int launch_model(const RunArgs& ra, void* stream) {
+  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO);
+  const long long grid = blocks_for(ra.m.M);
+  const int block = 32 * kWarpsPerBlock;
+  const size_t smem = ra.sp.bytes(kWarpsPerBlock);
+  switch (t) {
+    case PMOC_HAS_TW: return launch(k_model<LPL, PMOC_HAS_TW>, grid, block, smem, stream, ra);
+    case PMOC_HAS_SO: return launch(k_model<LPL, PMOC_HAS_SO>, grid, block, smem, stream, ra);
+    case PMOC_HAS_TW | PMOC_HAS_SO: return launch(k_model<LPL, PMOC_HAS_TW | PMOC_HAS_SO>, grid, block, smem, stream, ra);
+    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO:
+      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO>, grid, block, smem, stream, ra);
+    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO:
+      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO>, grid, block, smem, stream, ra);
+    default: return fail(PMOC_EUNSUPPORTED, "module combination has no fused kernel");
+  }
+}
+
+}  // namespace pmk
+
+#define PM_CAT2(a, b) a##b
+#define PM_CAT(a, b) PM_CAT2(a, b)
+int PM_CAT(pmoc_launch_model_, PM_LPL)(const RunArgs& ra, void* stream) { return launch_model<PM_LPL>(ra, stream); }

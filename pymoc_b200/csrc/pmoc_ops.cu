@@ -1,0 +1,299 @@
+// Per-module kernels and the C-ABI entry points of pymoc_b200 (see include/pymoc_b200.h).
+#include "pmoc_common.cuh"
+
+thread_local char pmoc_g_err[256] = "";
+
+namespace pmk {
+// ------------------------------------------------------------------------------------------
+// per-module kernels
+struct ColumnArgs {
+  long long M;
+  int nz;
+  const double* z;
+  pmoc_column col;
+  pmoc_vec wA, vdx_in, b_in;
+  double dt;
+  unsigned stages;
+};
+
+template <int LPL>
+PM_GLOBAL void k_column(ColumnArgs a) {
+  const int nz = a.nz, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
+  double* zs = rt::smem();
+  for (int i = W * 32 + L; i < 32 * LPL + 4; i += nthr) zs[i] = a.z[i < nz ? i : nz - 1];
+  rt::syncblock();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= a.M) return;
+  ColRegs<LPL> c;
+  col_load<LPL>(c, a.col, m, nz);
+  if (a.stages & PMOC_STAGE_CONVECT) pm::col_convect<LPL>(c.b, c.bs, c.N2min, zs, nz);
+  if (a.stages & PMOC_STAGE_VERTADVDIFF) {
+    double wA[LPL];
+    pm::load_lev<LPL>(wA, vrow(a.wA, m), nz, 0.0);
+    col_refold<LPL>(c, a.col, m, wA, zs, nz, a.dt);
+    if (!c.conv) pm::set_level<LPL>(c.b, nz - 1, c.bs);
+    c.conv = false;  // the convect stage (if any) already ran
+    col_advance<LPL>(c, zs, nz);
+  }
+  if (a.stages & PMOC_STAGE_HORADV)
+    pm::col_horadv<LPL>(c.b, vrow(a.vdx_in, m), vrow(a.b_in, m), vrow(a.col.Area, m), nz, a.dt);
+  pm::store_lev<LPL>(c.b, a.col.b + m * nz, nz);
+}
+
+struct ThermwindArgs {
+  long long M;
+  int nz, nb;
+  const double* z;
+  pmoc_vec b1, b2, f, gmid, Psi_in;
+  double *Psi, *psib, *bgrid, *iso_b, *iso_n;
+  int nzp, nbp;
+};
+
+template <int LPL>
+PM_GLOBAL void k_thermwind(ThermwindArgs a) {
+  const int nz = a.nz, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
+  double* zs = rt::smem();
+  for (int i = W * 32 + L; i < 32 * LPL + 4; i += nthr) zs[i] = a.z[i < nz ? i : nz - 1];
+  rt::syncblock();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= a.M) return;
+  double b1[LPL], b2[LPL], psi[LPL];
+  pm::load_lev<LPL>(b1, vrow(a.b1, m), nz, 0.0);
+  pm::load_lev<LPL>(b2, vrow(a.b2, m), nz, 0.0);
+  pm::tw_solve<LPL>(psi, b1, b2, vat(a.f, m), zs, nz, a.gmid.ptr ? vrow(a.gmid, m) : nullptr);
+  pm::store_lev<LPL>(psi, a.Psi + m * nz, nz);
+}
+
+template <int LPL>
+PM_GLOBAL void k_psib(ThermwindArgs a) {
+  const int nz = a.nz, nb = a.nb, L = rt::lane(), W = rt::warp_in_block();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= a.M) return;
+  double* ws = rt::smem() + (size_t)(3 * a.nzp + a.nbp) * W;
+  double b1[LPL], b2[LPL], psi[LPL];
+  pm::load_lev<LPL>(b1, vrow(a.b1, m), nz, 0.0);
+  pm::load_lev<LPL>(b2, vrow(a.b2, m), nz, 0.0);
+  pm::load_lev<LPL>(psi, vrow(a.Psi_in, m), nz, 0.0);
+  double* psib_s = ws + 3 * a.nzp;
+  const pm::BGrid G = pm::tw_psib<LPL>(psi, b1, b2, nz, nb, ws, ws + a.nzp, ws + 2 * a.nzp, psib_s);
+  for (int i = L; i < nb; i += 32) {
+    a.psib[m * nb + i] = psib_s[i];
+    if (a.bgrid) a.bgrid[m * nb + i] = G.at(i);
+  }
+  if (a.iso_b || a.iso_n) {
+    double ib[LPL], in_[LPL];
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const bool ok = pm::lev<LPL>(j) < nz;
+      ib[j] = ok ? pm::interp_bgrid(b1[j], G, psib_s) : 0.0;
+      in_[j] = ok ? pm::interp_bgrid(b2[j], G, psib_s) : 0.0;
+    }
+    if (a.iso_b) pm::store_lev<LPL>(ib, a.iso_b + m * nz, nz);
+    if (a.iso_n) pm::store_lev<LPL>(in_, a.iso_n + m * nz, nz);
+  }
+}
+
+struct SoArgs {
+  pmoc_model m;
+  pmoc_vec b, bs;
+  double *Psi, *Psi_Ek, *Psi_GM, *ys;
+  uint32_t* status;
+  int nzp, nyp;
+};
+
+template <int LPL>
+PM_GLOBAL void k_so(SoArgs a) {
+  const pmoc_model& M = a.m;
+  const int nz = M.nz, ny = M.ny, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
+  double* zs = rt::smem();
+  double* ysm = zs + a.nzp + 4;
+  double* bss = ysm + a.nyp + (size_t)a.nyp * W;
+  for (int i = W * 32 + L; i < a.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
+  for (int i = W * 32 + L; i < a.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
+  rt::syncblock();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= M.M) return;
+  const double* src = vrow(a.bs, m);
+  for (int i = L; i < a.nyp; i += 32) bss[i] = src[i < ny ? i : ny - 1];
+  rt::syncwarp();
+  pm::SoPar so{};
+  so.tau_ave = pm::mean100(vat(M.so_tau, m));
+  so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
+  so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
+  so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
+  double b[LPL], psi[LPL], ek[LPL], gm[LPL], ysv[LPL];
+  pm::load_lev<LPL>(b, vrow(a.b, m), nz, 0.0);
+  unsigned status = 0;
+  pm::so_solve<LPL>(psi, ek, gm, ysv, b, ysm, bss, ny, so, zs, nz, &status);
+  pm::store_lev<LPL>(psi, a.Psi + m * nz, nz);
+  if (a.Psi_Ek) pm::store_lev<LPL>(ek, a.Psi_Ek + m * nz, nz);
+  if (a.Psi_GM) pm::store_lev<LPL>(gm, a.Psi_GM + m * nz, nz);
+  if (a.ys) pm::store_lev<LPL>(ysv, a.ys + m * nz, nz);
+  if (a.status && L == 0) a.status[m] |= status;
+}
+
+static int lpl_for(int nz) { return nz <= 64 ? 2 : (nz + 31) / 32; }
+
+#define PM_DISPATCH_LPL(nz, CALL)                          \
+  switch (lpl_for(nz)) {                                   \
+    case 2: { constexpr int LPL = 2; CALL; } break;        \
+    case 3: { constexpr int LPL = 3; CALL; } break;        \
+    case 4: { constexpr int LPL = 4; CALL; } break;        \
+    case 5: { constexpr int LPL = 5; CALL; } break;        \
+    case 6: { constexpr int LPL = 6; CALL; } break;        \
+    case 7: { constexpr int LPL = 7; CALL; } break;        \
+    case 8: { constexpr int LPL = 8; CALL; } break;        \
+    default: return fail(PMOC_EUNSUPPORTED, "nz > 256 needs the block-per-member kernel"); \
+  }
+
+int check_column(const pmoc_column& c, const char* who) {
+  if (!c.b || !c.kappa.ptr || !c.dAk.ptr || !c.Area.ptr || !c.bs.ptr || !c.N2min.ptr || !c.bbot || c.nvar < 1)
+    return fail(PMOC_EINVAL, who);
+  return PMOC_OK;
+}
+
+int check_model(const pmoc_model* m) {
+  if (!m) return fail(PMOC_EINVAL, "model is NULL");
+  if (m->M <= 0 || m->nz < 3 || m->K < 1 || !m->z) return fail(PMOC_EINVAL, "bad M / nz / K / z");
+  const unsigned f = m->flags;
+  if (check_column(m->basin, "basin column incomplete")) return PMOC_EINVAL;
+  if ((f & PMOC_HAS_NORTH) && check_column(m->north, "north column incomplete")) return PMOC_EINVAL;
+  if ((f & PMOC_HAS_NORTH) && !((f & PMOC_HAS_TW) && (f & PMOC_ISO)))
+    return fail(PMOC_EINVAL, "a north column needs PMOC_HAS_TW | PMOC_ISO");
+  if ((f & PMOC_ISO) && !(f & PMOC_HAS_TW)) return fail(PMOC_EINVAL, "PMOC_ISO needs PMOC_HAS_TW");
+  if (f & PMOC_HAS_TW) {
+    if (!m->tw_f.ptr) return fail(PMOC_EINVAL, "tw_f missing");
+    if (!(f & PMOC_HAS_NORTH) && !m->tw_b2.ptr) return fail(PMOC_EINVAL, "tw_b2 missing");
+    if ((f & PMOC_ISO) && (!m->Psi_iso_b || !m->Psi_iso_n || m->nb < 2))
+      return fail(PMOC_EINVAL, "Psi_iso_b / Psi_iso_n / nb missing");
+    if (!(f & PMOC_ISO) && !m->Psi_tw) return fail(PMOC_EINVAL, "Psi_tw missing");
+  }
+  if (f & PMOC_HAS_SO) {
+    if (!m->y || m->ny < 2 || !m->so_tau.ptr || !m->so_f.ptr || !m->so_rho.ptr || !m->so_L.ptr || !m->so_KGM.ptr ||
+        !m->so_smax.ptr || !m->so_sill_taper || !m->so_ek_taper || !m->so_top_taper || !m->so_bot_taper || !m->Psi_so)
+      return fail(PMOC_EINVAL, "Psi_SO parameters incomplete");
+    if (!(f & PMOC_HAS_ML) && !m->so_bs.ptr) return fail(PMOC_EINVAL, "so_bs missing");
+    if (m->so_tau_on_y) return fail(PMOC_EUNSUPPORTED, "tau on the y grid is not implemented yet");
+    if (m->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "F2010 BVP smoother (c != None) is not implemented yet");
+  }
+  if (f & (PMOC_HAS_ML | PMOC_ORDER_JN)) return fail(PMOC_EUNSUPPORTED, "SO_ML / 'jn' order not implemented yet");
+  return PMOC_OK;
+}
+
+int run_model(const pmoc_model* m, long long it0, long long nsteps, int diagnose_only, void* stream) {
+  if (int rc = check_model(m)) return rc;
+  if (nsteps < 0 || it0 < 0) return fail(PMOC_EINVAL, "negative it0 / nsteps");
+  if (!diagnose_only && nsteps == 0) return PMOC_OK;
+  RunArgs ra;
+  ra.m = *m;
+  ra.it0 = it0;
+  ra.nsteps = nsteps;
+  ra.diagnose_only = diagnose_only;
+  const int lpl = lpl_for(m->nz);
+  ra.sp = plan_smem(lpl, m->ny, m->nb, m->flags);
+  switch (lpl) {
+    case 2: return pmoc_launch_model_2(ra, stream);
+    case 3: return pmoc_launch_model_3(ra, stream);
+    case 4: return pmoc_launch_model_4(ra, stream);
+    case 5: return pmoc_launch_model_5(ra, stream);
+    case 6: return pmoc_launch_model_6(ra, stream);
+    case 7: return pmoc_launch_model_7(ra, stream);
+    case 8: return pmoc_launch_model_8(ra, stream);
+    default: return fail(PMOC_EUNSUPPORTED, "nz > 256 needs the block-per-member kernel");
+  }
+}
+
+}  // namespace pmk
+
+// ==========================================================================================
+extern "C" {
+
+int pmoc_abi_version(void) { return PMOC_ABI_VERSION; }
+const char* pmoc_last_error(void) { return g_err; }
+
+int pmoc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+#ifdef PMOC_EMU
+  if (sm_count) *sm_count = 0;
+  if (cc_major) *cc_major = 0;
+  if (cc_minor) *cc_minor = 0;
+  return PMOC_OK;
+#else
+  int dev = 0;
+  PM_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  PM_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return PMOC_OK;
+#endif
+}
+
+int pmoc_model_diagnose(const pmoc_model* m, void* stream) { return run_model(m, 0, 0, 1, stream); }
+
+int pmoc_model_run(const pmoc_model* m, int64_t it0, int64_t nsteps, void* stream) {
+  return run_model(m, it0, nsteps, 0, stream);
+}
+
+int pmoc_column_timestep(int64_t M, int32_t nz, const double* z, const pmoc_column* col, pmoc_vec wA, pmoc_vec vdx_in,
+                         pmoc_vec b_in, double dt, uint32_t stages, void* stream) {
+  if (M <= 0 || nz < 3 || !z || !col) return fail(PMOC_EINVAL, "bad M / nz / z / col");
+  if (check_column(*col, "column incomplete")) return PMOC_EINVAL;
+  if ((stages & PMOC_STAGE_VERTADVDIFF) && !wA.ptr) return fail(PMOC_EINVAL, "wA missing");
+  if ((stages & PMOC_STAGE_HORADV) && (!vdx_in.ptr || !b_in.ptr)) return fail(PMOC_EINVAL, "vdx_in / b_in missing");
+  ColumnArgs a{M, nz, z, *col, wA, vdx_in, b_in, dt, stages};
+  PM_DISPATCH_LPL(nz, return launch(k_column<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
+                                    sizeof(double) * (32 * LPL + 4), stream, a));
+  return PMOC_OK;
+}
+
+int pmoc_thermwind_solve(int64_t M, int32_t nz, const double* z, pmoc_vec b1, pmoc_vec b2, pmoc_vec f, pmoc_vec gmid,
+                         double* Psi, void* stream) {
+  if (M <= 0 || nz < 3 || !z || !b1.ptr || !b2.ptr || !f.ptr || !Psi) return fail(PMOC_EINVAL, "bad thermwind arguments");
+  ThermwindArgs a{};
+  a.M = M; a.nz = nz; a.z = z; a.b1 = b1; a.b2 = b2; a.f = f; a.gmid = gmid; a.Psi = Psi;
+  PM_DISPATCH_LPL(nz, return launch(k_thermwind<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
+                                    sizeof(double) * (32 * LPL + 4), stream, a));
+  return PMOC_OK;
+}
+
+int pmoc_thermwind_psib(int64_t M, int32_t nz, int32_t nb, pmoc_vec Psi, pmoc_vec b1, pmoc_vec b2, double* psib,
+                        double* bgrid, double* iso_b, double* iso_n, void* stream) {
+  if (M <= 0 || nz < 3 || nb < 2 || !Psi.ptr || !b1.ptr || !b2.ptr || !psib) return fail(PMOC_EINVAL, "bad psib arguments");
+  ThermwindArgs a{};
+  a.M = M; a.nz = nz; a.nb = nb; a.Psi_in = Psi; a.b1 = b1; a.b2 = b2;
+  a.psib = psib; a.bgrid = bgrid; a.iso_b = iso_b; a.iso_n = iso_n;
+  a.nbp = (nb + 3) & ~3;
+  PM_DISPATCH_LPL(nz, {
+    a.nzp = 32 * LPL;
+    return launch(k_psib<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
+                  sizeof(double) * (size_t)(3 * a.nzp + a.nbp) * kWarpsPerBlock, stream, a);
+  });
+  return PMOC_OK;
+}
+
+int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, double* Psi_Ek, double* Psi_GM, double* ys,
+                  uint32_t* status, void* stream) {
+  if (!so || so->M <= 0 || so->nz < 3 || so->ny < 2 || !so->z || !so->y || !b.ptr || !bs.ptr || !Psi)
+    return fail(PMOC_EINVAL, "bad Psi_SO arguments");
+  if (!so->so_tau.ptr || !so->so_f.ptr || !so->so_rho.ptr || !so->so_L.ptr || !so->so_KGM.ptr || !so->so_smax.ptr ||
+      !so->so_sill_taper || !so->so_ek_taper || !so->so_top_taper || !so->so_bot_taper)
+    return fail(PMOC_EINVAL, "Psi_SO parameters incomplete");
+  if (so->so_tau_on_y) return fail(PMOC_EUNSUPPORTED, "tau on the y grid is not implemented yet");
+  if (so->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "F2010 BVP smoother (c != None) is not implemented yet");
+  SoArgs a{};
+  a.m = *so; a.b = b; a.bs = bs; a.Psi = Psi; a.Psi_Ek = Psi_Ek; a.Psi_GM = Psi_GM; a.ys = ys; a.status = status;
+  a.nyp = (so->ny + 3) & ~3;
+  PM_DISPATCH_LPL(so->nz, {
+    a.nzp = 32 * LPL;
+    return launch(k_so<LPL>, blocks_for(so->M), 32 * kWarpsPerBlock,
+                  sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + a.nyp * kWarpsPerBlock), stream, a);
+  });
+  return PMOC_OK;
+}
+
+int pmoc_ml_timestep(const pmoc_model*, pmoc_vec, pmoc_vec, double, uint32_t*, void*) {
+  return fail(PMOC_EUNSUPPORTED, "SO_ML is not implemented yet");
+}
+
+}  // extern "C"

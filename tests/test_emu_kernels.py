@@ -1,0 +1,27 @@
+"""Kernel-logic tests on the GPU-less build box (CPU only).
+
+The product kernel sources are compiled with g++ against the warp emulator in tests/emu/
+(test infrastructure, not a fallback) and driven through the same C ABI and the same
+Python front end as on the GPU; results are compared with the golden fixtures produced by
+the reference.  The GPU parity tests proper are in test_gpu_parity.py.
+"""
+import numpy as np
+import pytest
+
+from emu.emu_backend import EmuBackend
+from parity_common import run_against_golden
+
+
+@pytest.fixture(scope='module')
+def emu():
+  return EmuBackend()
+
+
+@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 720), ('twocol', 480), ('c3', 480)])
+def test_fused_kernel_vs_reference(emu, name, nmax):
+  run_against_golden(emu, name, nmax)
+
+
+@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25)])
+def test_short_launches_carry_streamfunctions(emu, name, nmax):
+  run_against_golden(emu, name, nmax, chunked=True)

@@ -1,0 +1,97 @@
+"""GPU parity tests proper: the C ABI of libpymoc_b200.so on cuda:0 vs the reference.
+
+Golden fixtures come from the unmodified reference (tests/golden/make_golden.py); the live
+oracle (oracle/pymoc_oracle.py, pinned to the same fixtures) covers members the fixtures
+do not hold.  Tolerance: 1e-10 relative, max-norm per field (north_star, explicit path).
+"""
+import ctypes
+import warnings
+
+import numpy as np
+import pytest
+
+from helpers import relmax
+from parity_common import TOL, run_against_golden
+
+pytestmark = pytest.mark.gpu
+warnings.filterwarnings('ignore', category=RuntimeWarning)
+
+
+@pytest.fixture(scope='module')
+def cuda():
+  from pymoc_b200.backend import CudaBackend
+  return CudaBackend()
+
+
+@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 2160), ('twocol', 480), ('c3', 2400)])
+def test_fused_kernel_vs_reference(cuda, name, nmax):
+  worst = run_against_golden(cuda, name, nmax)
+  print('%s: worst relative error %.2e' % (name, worst))
+
+
+@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25)])
+def test_short_launches_carry_streamfunctions(cuda, name, nmax):
+  run_against_golden(cuda, name, nmax, chunked=True)
+
+
+def test_ensemble_members_vs_live_oracle(cuda):
+  """A 256-member tau x kappa x bs_north x A lattice of the C3 model: sampled members against
+  the oracle, and the whole ensemble for finiteness and lattice symmetry."""
+  from oracle import pymoc_oracle as O
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  spec = configs.c3_twocol_so(256, axes=(4, 4, 4, 4))
+  ens = Ensemble(spec, backend=cuda)
+  ens.run(121)
+  got = {**ens.state(), **ens.diagnostics()}
+  assert np.isfinite(got['b_basin']).all() and np.isfinite(got['Psi_iso_b']).all()
+  for m in (0, 37, 101, 200, 255):
+    want = O.run_coupled(spec.member_case(m), 121, O.REFERENCE)
+    for key in ('b_basin', 'b_north', 'Psi_tw', 'Psi_iso_b', 'Psi_iso_n', 'Psi_so', 'psib'):
+      assert relmax(got[key][m], want[key]) < TOL, (m, key, relmax(got[key][m], want[key]))
+
+
+def test_full_size_properties(cuda):
+  """BASELINE size (65,536 members, nz=200): size-independent properties.
+  (1) duplicated parameters give bit-identical members; (2) splitting a run into launches
+  changes nothing bit-wise; (3) the surface/bottom boundary values are the exact copies the
+  reference makes (b[-1] == bs, b[0] == bbot); (4) Psi_so[0] == 0."""
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  spec = configs.c2_column_so(65536)
+  a = Ensemble(spec, backend=cuda)
+  a.run(145)
+  b = Ensemble(spec, backend=cuda)
+  b.run(72)
+  b.run(1)
+  b.run(72)
+  sa, sb = a.state()['b_basin'], b.state()['b_basin']
+  assert np.array_equal(sa, sb)
+  assert np.array_equal(a.diagnostics()['Psi_so'], b.diagnostics()['Psi_so'])
+  assert np.all(sa[:, -1] == 0.03) and np.all(sa[:, 0] == 0.0)
+  assert np.all(a.diagnostics()['Psi_so'][:, 0] == 0.0)
+  # members 0..255 share tau (first lattice axis) but not kappa: all distinct
+  assert len({sa[i].tobytes() for i in range(256)}) == 256
+  assert np.isfinite(sa).all()
+
+
+def test_host_buffer_entry_point(cuda):
+  """pmoc_model_run_host (host pointers, copies inside) == device path, bit for bit."""
+  from emu.emu_backend import EmuBackend  # only for its numpy buffer handling
+  from pymoc_b200 import _lib, configs
+  from pymoc_b200.ensemble import Ensemble
+
+  class HostBuffers(EmuBackend):
+    def __init__(self, lib):
+      self.lib = lib
+
+  spec = configs.c3_twocol_so(16, axes=(2, 2, 2, 2))
+  dev = Ensemble(spec, backend=cuda)
+  dev.run(30)
+  host = Ensemble(spec, backend=HostBuffers(cuda.lib))
+  _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 0, 13))
+  _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 13, 17))
+  for key, val in dev.state().items():
+    assert np.array_equal(val, host.state()[key]), key
+  for key in ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib'):
+    assert np.array_equal(dev.diagnostics()[key], host.diagnostics()[key]), key
