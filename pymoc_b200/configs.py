@@ -117,8 +117,8 @@ def c3_twocol_so(M=262144, c=None, axes=None):
     nt, nk, nn, na = axes
     sweep = lattice(tau=np.linspace(0.05, 0.25, nt) if nt > 1 else [0.13],
                     kappa=np.geomspace(1e-5, 1e-4, nk) if nk > 1 else [2e-5],
-                    bs_north=np.linspace(0.002, 0.006, nn) if nn > 1 else [0.004],
-                    A_basin=np.linspace(4e13, 8e13, na) if na > 1 else [6e13])
+                    bs_north=np.linspace(0.002, 0.0045, nn) if nn > 1 else [0.004],
+                    A_basin=np.linspace(6e13, 1.2e14, na) if na > 1 else [6e13])
   assert sweep['tau'].size == M, (sweep['tau'].size, M)
   kappa = sweep['kappa'][:, None] + 0 * z[None, :]
   A_b = sweep['A_basin'][:, None] + 0 * z[None, :]

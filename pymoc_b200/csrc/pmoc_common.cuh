@@ -36,34 +36,55 @@ PM_DEV const double* vrow(const pmoc_vec& v, long long m) { return v.ptr + m * v
 constexpr int kWarpsPerBlock = 4;
 
 // ------------------------------------------------------------------------------------------
-// shared-memory plan of k_model (in doubles)
+// shared-memory plan (in doubles).  Per block: the grid tables; per warp (= member): the
+// column tables and the scratch of the diagnostics.
 struct SmemPlan {
   int nzp, nyp, nbp;
-  int off_z, off_y;        // per block
-  int off_warp0, per_warp; // per warp region
-  int w_ctop, w_crinv, w_cu, w_psib, w_bs;
-  size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
+  int off_zs, off_zl, off_rdu, off_rdd, off_ruu, off_rdd2, off_y;  // per block
+  int off_warp0, per_warp;                                          // per warp region
+  int w_col[2];                                                     // ColTab of basin / north (4*nzp each)
+  int w_ctop, w_crinv, w_cu, w_psib, w_bs, w_sinv;
+  PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
 
-static inline SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
+static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   SmemPlan s{};
   s.nzp = 32 * LPL;
   s.nyp = (ny + 3) & ~3;
   s.nbp = (nb + 3) & ~3;
   int o = 0;
-  s.off_z = o; o += s.nzp + 4;
+  s.off_zs = o; o += s.nzp + 4;
+  s.off_zl = o; o += s.nzp;
+  s.off_rdu = o; o += s.nzp;
+  s.off_rdd = o; o += s.nzp;
+  s.off_ruu = o; o += s.nzp;
+  s.off_rdd2 = o; o += s.nzp;
   s.off_y = o; o += s.nyp;
   s.off_warp0 = o;
   int w = 0;
+  s.w_col[0] = w; w += 4 * s.nzp;
+  if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += 4 * s.nzp; }
   if (flags & PMOC_ISO) {
     s.w_ctop = w; w += s.nzp;
     s.w_crinv = w; w += s.nzp;
     s.w_cu = w; w += s.nzp;
     s.w_psib = w; w += s.nbp;
   }
-  if (flags & PMOC_HAS_SO) { s.w_bs = w; w += s.nyp; }
+  if (flags & PMOC_HAS_SO) {
+    s.w_bs = w; w += s.nyp;
+    s.w_sinv = w; w += s.nyp;
+  }
   s.per_warp = w;
   return s;
+}
+
+PM_DEV pm::GeoTab geo_of(double* sm, const SmemPlan& sp) {
+  return pm::GeoTab{sm + sp.off_zs, sm + sp.off_zl, sm + sp.off_rdu, sm + sp.off_rdd, sm + sp.off_ruu,
+                    sm + sp.off_rdd2};
+}
+PM_DEV pm::ColTab coltab_of(double* ws, const SmemPlan& sp, int which) {
+  double* t = ws + sp.w_col[which];
+  return pm::ColTab{t, t + sp.nzp, t + 2 * sp.nzp, t + 3 * sp.nzp};
 }
 
 struct RunArgs {
@@ -78,8 +99,9 @@ template <int LPL>
 struct ColRegs {
   double b[LPL], p[LPL], q[LPL];
   double bs, N2min, bbot, bzbot;
-  bool has_bzbot, conv;
+  bool has_bzbot, conv, plain;  // plain: neither convection nor a gradient bottom condition
   int var;
+  pm::ColTab tab;
 };
 
 template <int LPL>
@@ -91,26 +113,37 @@ PM_DEV void col_load(ColRegs<LPL>& c, const pmoc_column& d, long long m, int nz)
   c.has_bzbot = d.bzbot.ptr != nullptr;
   c.bzbot = c.has_bzbot ? vat(d.bzbot, m) : 0.0;
   c.conv = d.do_conv != 0;
+  c.plain = !c.conv && !c.has_bzbot;
   c.var = (d.var != nullptr && d.nvar > 1) ? d.var[m] : 0;
 }
 
+// (re)build the member's coefficient tables for the kappa variant in use
 template <int LPL>
-PM_DEV void col_refold(ColRegs<LPL>& c, const pmoc_column& d, long long m, const double (&wA)[LPL],
-                       const double* zs, int nz, double dt) {
+PM_DEV void col_retabulate(ColRegs<LPL>& c, const pmoc_column& d, long long m, const pm::GeoTab& G, int nz,
+                           double dt) {
   const long long voff = (long long)c.var * nz;
-  pm::col_coeffs<LPL>(c.p, c.q, wA, vrow(d.kappa, m) + voff, vrow(d.dAk, m) + voff, vrow(d.Area, m), zs, nz, dt);
+  pm::col_tabulate<LPL>(c.tab, G, vrow(d.kappa, m) + voff, vrow(d.dAk, m) + voff, vrow(d.Area, m), nz, dt);
 }
 
-// Column.timestep(wA, dt, do_conv) as the loop calls it (column.py:336-341)
+// bottom boundary condition of vertadvdiff (column.py:232-233)
 template <int LPL>
-PM_DEV void col_advance(ColRegs<LPL>& c, const double* zs, int nz) {
-  if (c.conv) pm::col_convect<LPL>(c.b, c.bs, c.N2min, zs, nz);
+PM_DEV void col_bottom(ColRegs<LPL>& c, const double* zs) {
   if (rt::lane() == 0) {
-    if (c.has_bzbot) {
-      if (LPL > 1) c.b[0] = c.b[LPL > 1 ? 1 : 0] - c.bzbot * (zs[1] - zs[0]);
-    } else {
+    if (c.has_bzbot)
+      c.b[0] = c.b[LPL > 1 ? 1 : 0] - c.bzbot * (zs[1] - zs[0]);
+    else
       c.b[0] = c.bbot;
-    }
+  }
+}
+
+// Column.timestep(wA, dt, do_conv) as the loop calls it (column.py:336-341).  For a "plain"
+// column the boundary values are invariant under the step (p = q = 0 there) and are set once
+// per launch, so the step is the bare stencil.
+template <int LPL>
+PM_DEV void col_advance(ColRegs<LPL>& c, const pm::GeoTab& G, int nz) {
+  if (!c.plain) {
+    if (c.conv) pm::col_convect<LPL>(c.b, c.bs, c.N2min, G.zs, G.zl, nz);
+    col_bottom<LPL>(c, G.zs);
   }
   pm::col_step<LPL>(c.b, c.p, c.q);
 }

@@ -20,6 +20,17 @@ constexpr double kSv = 1e6;
 
 template <int LPL>
 PM_DEV int lev(int j) { return rt::lane() * LPL + j; }
+// per-warp shared arrays that are only ever read by their owner use the conflict-free
+// lane-major layout: slot j of lane L lives at j*32 + L
+PM_DEV int lm(int j) { return j * 32 + rt::lane(); }
+
+// x / c for a constant c with rc = 1/c pre-rounded: product, exact residual, one correction
+// (Markstein).  Correctly rounded -- the same bits as the IEEE divide the reference performs --
+// whenever no intermediate over/underflows; checked against x / 1e6 on 4e8 random doubles.
+PM_DEV double div_const(double x, double c, double rc) {
+  const double q = x * rc;
+  return rt::fma(rt::fma(-c, q, x), rc, q);
+}
 
 // registers <- natural-order global/shared array
 template <int LPL>
@@ -56,28 +67,81 @@ PM_DEV double wscan_excl(double v) {
 //   b_i += dt*( -weff_i * (weff_i<0 ? d_i/dzu : d_{i-1}/dzd) / A_i
 //               + kappa_i * (d_i/dzu - d_{i-1}/dzd) / (0.5*(dzu+dzd)) )  =  p_i d_i - q_i d_{i-1}
 // weff = wA - d(A kappa)/dz is fixed between two streamfunction updates, so p, q are rebuilt
-// only then.  Boundary and padding levels get p = q = 0.
+// only then.  Everything state-independent is tabulated once per launch:
+//   per block  (GeoTab, lane-major): 1/dzu, 1/dzd, 1/(dzc dzu), 1/(dzc dzd), z
+//   per member (ColTab, lane-major): KU = dt kappa/(dzc dzu), KD = dt kappa/(dzc dzd), RA = dt/A, dAk
+// Boundary and padding levels get p = q = 0.
+struct GeoTab {
+  const double *zs;                      // natural order, nzp+4 (padded with z[nz-1])
+  const double *zl, *rdu, *rdd, *ruu, *rdd2;  // lane-major, nzp each
+};
+struct ColTab {
+  double *ku, *kd, *ra, *dak;  // lane-major, nzp each (per warp)
+};
+
+// block-cooperative fill of the geometry tables (call before the block barrier)
 template <int LPL>
-PM_DEV void col_coeffs(double (&p)[LPL], double (&q)[LPL], const double (&wA)[LPL],
-                       const double* PM_RESTRICT kappa, const double* PM_RESTRICT dAk,
-                       const double* PM_RESTRICT Area, const double* zs, int nz, double dt) {
+PM_DEV void geo_fill(double* zs, double* zl, double* rdu, double* rdd, double* ruu, double* rdd2,
+                     const double* PM_RESTRICT z, int nz, int tid, int nthr) {
+  const int nzp = 32 * LPL;
+  for (int i = tid; i < nzp + 4; i += nthr) zs[i] = z[i < nz ? i : nz - 1];
+  for (int s = tid; s < nzp; s += nthr) {
+    const int L = s & 31, j = s >> 5, i = L * LPL + j;
+    double a = 0., b = 0., c = 0., d = 0.;
+    if (i >= 1 && i < nz - 1) {
+      const double dzu = z[i + 1] - z[i], dzd = z[i] - z[i - 1], dzc = 0.5 * (dzu + dzd);
+      a = 1. / dzu;
+      b = 1. / dzd;
+      c = 1. / (dzc * dzu);
+      d = 1. / (dzc * dzd);
+    }
+    zl[s] = z[i < nz ? i : nz - 1];
+    rdu[s] = a;
+    rdd[s] = b;
+    ruu[s] = c;
+    rdd2[s] = d;
+  }
+}
+
+// per-member tables from the (host-sampled) kappa, d(A kappa)/dz and Area profiles
+template <int LPL>
+PM_DEV void col_tabulate(const ColTab& T, const GeoTab& G, const double* PM_RESTRICT kappa,
+                         const double* PM_RESTRICT dAk, const double* PM_RESTRICT Area, int nz, double dt) {
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
-    const int i = lev<LPL>(j);
+    const int i = lev<LPL>(j), s = lm(j);
+    double ku = 0., kd = 0., ra = 0., dk = 0.;
+    if (i >= 1 && i < nz - 1) {
+      const double kdt = dt * kappa[i];
+      ku = kdt * G.ruu[s];
+      kd = kdt * G.rdd2[s];
+      ra = dt / Area[i];
+      dk = dAk[i];
+    }
+    T.ku[s] = ku;
+    T.kd[s] = kd;
+    T.ra[s] = ra;
+    T.dak[s] = dk;
+  }
+  rt::syncwarp();
+}
+
+template <int LPL>
+PM_DEV void col_coeffs(double (&p)[LPL], double (&q)[LPL], const double (&wA)[LPL], const ColTab& T,
+                       const GeoTab& G, int nz) {
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j), s = lm(j);
     double pj = 0.0, qj = 0.0;
     if (i >= 1 && i < nz - 1) {
-      const double zc = zs[i];
-      const double dzu = zs[i + 1] - zc, dzd = zc - zs[i - 1];
-      const double dzc = 0.5 * (dzu + dzd);
-      const double weff = wA[j] - dAk[i];
-      const double kdt = dt * kappa[i];
-      const double adt = dt / Area[i];
-      pj = kdt / (dzc * dzu);
-      qj = kdt / (dzc * dzd);
+      const double weff = wA[j] - T.dak[s];
+      const double ra = T.ra[s];
+      pj = T.ku[s];
+      qj = T.kd[s];
       if (weff < 0)
-        pj = pj - weff * (adt / dzu);
+        pj = pj - weff * (ra * G.rdu[s]);
       else
-        qj = qj + weff * (adt / dzd);
+        qj = qj + weff * (ra * G.rdd[s]);
     }
     p[j] = pj;
     q[j] = qj;
@@ -100,7 +164,7 @@ PM_DEV void col_step(double (&b)[LPL], const double (&p)[LPL], const double (&q)
 
 // Convective adjustment (column.py:264-271).  Strict '>' and un-fused bs + N2min*(z - zconv).
 template <int LPL>
-PM_DEV void col_convect(double (&b)[LPL], double bs, double N2min, const double* zs, int nz) {
+PM_DEV void col_convect(double (&b)[LPL], double bs, double N2min, const double* zs, const double* zl, int nz) {
   unsigned mine = 0;
   int top_stable = -1;
   PM_UNROLL
@@ -118,7 +182,7 @@ PM_DEV void col_convect(double (&b)[LPL], double bs, double N2min, const double*
     const double zc = zs[anchor >= 0 ? anchor : 0];
     PM_UNROLL
     for (int j = 0; j < LPL; ++j)
-      if ((mine >> j) & 1u) b[j] = bs + N2min * (zs[lev<LPL>(j)] - zc);
+      if ((mine >> j) & 1u) b[j] = bs + N2min * (zl[lm(j)] - zc);
   } else {
     PM_UNROLL
     for (int j = 0; j < LPL; ++j)
@@ -203,7 +267,7 @@ PM_DEV void tw_solve(double (&psi)[LPL], const double (&b1)[LPL], const double (
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
-    psi[j] = i < nz ? (part[j] - total * ((zs[i] - z0) / H)) / kSv : 0.0;
+    psi[j] = i < nz ? div_const(part[j] - total * ((zs[i] - z0) / H), kSv, 1.0 / kSv) : 0.0;
   }
 }
 
@@ -404,8 +468,10 @@ PM_DEV double outcrop_brent(double bval, const double* ygrid, const double* bs, 
   return xcur;
 }
 
-// Unique root of the piecewise-linear bs(y) = bval when bs is non-decreasing north of its minimum
-PM_DEV double outcrop_monotone(double bval, const double* ygrid, const double* bs, int ny, int south) {
+// Unique root of the piecewise-linear bs(y) = bval when bs is non-decreasing north of its
+// minimum.  sinv[k] = (y[k+1]-y[k])/(bs[k+1]-bs[k]) is tabulated with the surface scan.
+PM_DEV double outcrop_monotone(double bval, const double* ygrid, const double* bs, const double* sinv, int ny,
+                               int south) {
   if (bs[south] == bval) return ygrid[south];
   if (bs[ny - 1] == bval) return ygrid[ny - 1];
   int lo = south, hi = ny - 1;  // first index with bs >= bval lies in (south, ny-1]
@@ -417,7 +483,7 @@ PM_DEV double outcrop_monotone(double bval, const double* ygrid, const double* b
       lo = mid;
   }
   if (bs[hi] == bval) return ygrid[hi];
-  return ygrid[hi - 1] + (bval - bs[hi - 1]) * (ygrid[hi] - ygrid[hi - 1]) / (bs[hi] - bs[hi - 1]);
+  return ygrid[hi - 1] + (bval - bs[hi - 1]) * sinv[hi - 1];
 }
 
 // np.mean(tau + 0*np.linspace(y0, yN, 100)) for a float tau (psi_SO.py:239): numpy's pairwise
@@ -439,7 +505,9 @@ struct SoSurf {  // per-refresh scan of bs(y)
   int south;
   bool mono;
 };
-PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, int ny) {
+// Scan of the surface buoyancy: minimum / argmin (first occurrence, np.argmin), monotonicity
+// north of it, and the inverse segment slopes.  Warp-cooperative; redone only when bs changes.
+PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int ny) {
   SoSurf s;
   s.mn = bs[0];
   s.south = 0;
@@ -448,23 +516,28 @@ PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, int ny) {
       s.mn = bs[k];
       s.south = k;
     }
-  s.mono = true;
-  for (int k = s.south; k < ny - 1; ++k)
-    if (bs[k + 1] < bs[k]) s.mono = false;
+  bool down = false;
+  for (int k = rt::lane(); k < ny - 1; k += 32) {
+    const double db = bs[k + 1] - bs[k];
+    sinv[k] = (ygrid[k + 1] - ygrid[k]) / db;
+    if (k >= s.south && db < 0) down = true;
+  }
+  s.mono = rt::ballot(down) == 0;
   s.bsN = bs[ny - 1];
   s.y0 = ygrid[0];
   s.yN = ygrid[ny - 1];
+  rt::syncwarp();
   return s;
 }
 
 // Psi_SO.solve with the explicit GM branch (psi_SO.py:106-140, 218-243, 302-354).  Sv.
 template <int LPL>
 PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], double (&ysv)[LPL],
-                     const double (&b)[LPL], const double* ygrid, const double* bs, int ny, const SoPar& P,
-                     const double* zs, int nz, unsigned* status) {
-  const SoSurf S = so_scan(ygrid, bs, ny);
+                     const double (&b)[LPL], const double* ygrid, const double* bs, const double* sinv, int ny,
+                     const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status) {
   if (!S.mono) *status |= 2u;
   const double pre = P.tau_ave / P.f / P.rho * P.L;
+  const double c6 = 1e6, r6 = 1.0 / 1e6;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
@@ -476,13 +549,13 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
       else if (bi > S.bsN)
         yo = S.yN;
       else if (S.mono)
-        yo = outcrop_monotone(bi, ygrid, bs, ny, S.south);
+        yo = outcrop_monotone(bi, ygrid, bs, sinv, ny, S.south);
       else {
         bool bad = false;
         yo = outcrop_brent(bi, ygrid, bs, ny, S.south, &bad);
         if (bad) *status |= 4u;
       }
-      e = pre * P.sill[i] * P.ektap[i] / 1e6;
+      e = div_const(pre * P.sill[i] * P.ektap[i], c6, r6);
       double dy = S.yN - yo;
       dy = 0.1 > dy ? 0.1 : dy;
       const double s = zs[i] / dy, ms = -P.smax;
@@ -492,7 +565,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
         const double alt = -e * 1e6;
         t = (t >= alt || t != t) ? t : alt;
       }
-      g = t / 1e6;
+      g = div_const(t, c6, r6);
       ps = i == 0 ? 0. : e + g;
     }
     ek[j] = e;

@@ -8,7 +8,7 @@
 
 namespace pmk {
 template <int LPL, unsigned TOPO>
-PM_GLOBAL void k_model(RunArgs a) {
+PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   const pmoc_model& M = a.m;
@@ -16,23 +16,33 @@ PM_GLOBAL void k_model(RunArgs a) {
   const int nz = M.nz, ny = M.ny, nb = M.nb;
   const int L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
   double* sm = rt::smem();
-  double* zs = sm + sp.off_z;
   double* ysm = sm + sp.off_y;
   double* ws = sm + sp.off_warp0 + (size_t)sp.per_warp * W;
-  for (int i = W * 32 + L; i < sp.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
+  pm::geo_fill<LPL>(sm + sp.off_zs, sm + sp.off_zl, sm + sp.off_rdu, sm + sp.off_rdd, sm + sp.off_ruu,
+                    sm + sp.off_rdd2, M.z, nz, W * 32 + L, nthr);
   if (SO)
     for (int i = W * 32 + L; i < sp.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
   rt::syncblock();
+  const pm::GeoTab G = geo_of(sm, sp);
+  const double* zs = G.zs;
   const long long m = rt::block_idx() * rt::warps_per_block() + W;
   if (m >= M.M) return;
+  const double dt = M.dt;
 
   ColRegs<LPL> cb, cn;
   col_load<LPL>(cb, M.basin, m, nz);
-  if (NORTH) col_load<LPL>(cn, M.north, m, nz);
+  cb.tab = coltab_of(ws, sp, 0);
+  col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
+  if (NORTH) {
+    col_load<LPL>(cn, M.north, m, nz);
+    cn.tab = coltab_of(ws, sp, 1);
+    col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
+  }
   double b2fix[LPL];
   if (TW && !NORTH) pm::load_lev<LPL>(b2fix, vrow(M.tw_b2, m), nz, 0.0);
   const double tw_f = TW ? vat(M.tw_f, m) : 1.0;
   pm::SoPar so{};
+  pm::SoSurf surf{};
   if (SO) {
     so.tau_ave = pm::mean100(vat(M.so_tau, m));
     so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
@@ -41,9 +51,9 @@ PM_GLOBAL void k_model(RunArgs a) {
     const double* src = vrow(M.so_bs, m);
     for (int i = L; i < sp.nyp; i += 32) ws[sp.w_bs + i] = src[i < ny ? i : ny - 1];
     rt::syncwarp();
+    surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);  // bs(y) is fixed without a mixed layer
   }
   unsigned status = 0;
-  const double dt = M.dt;
 
   // Diagnose the streamfunctions from the current state and fold them into the stencils.
   auto refresh = [&](bool write) {
@@ -54,13 +64,13 @@ PM_GLOBAL void k_model(RunArgs a) {
       if (write && M.Psi_tw) pm::store_lev<LPL>(psi_tw, M.Psi_tw + m * nz, nz);
       if (ISO) {
         double* psib_s = ws + sp.w_psib;
-        const pm::BGrid G = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_ctop, ws + sp.w_crinv,
-                                             ws + sp.w_cu, psib_s);
+        const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_ctop, ws + sp.w_crinv,
+                                              ws + sp.w_cu, psib_s);
         PM_UNROLL
         for (int j = 0; j < LPL; ++j) {
           const bool ok = pm::lev<LPL>(j) < nz;
-          iso_b[j] = ok ? pm::interp_bgrid(cb.b[j], G, psib_s) : 0.0;
-          iso_n[j] = ok ? pm::interp_bgrid(b2[j], G, psib_s) : 0.0;
+          iso_b[j] = ok ? pm::interp_bgrid(cb.b[j], BG, psib_s) : 0.0;
+          iso_n[j] = ok ? pm::interp_bgrid(b2[j], BG, psib_s) : 0.0;
         }
         if (write) {
           pm::store_lev<LPL>(iso_b, M.Psi_iso_b + m * nz, nz);
@@ -68,14 +78,14 @@ PM_GLOBAL void k_model(RunArgs a) {
           if (M.psib)
             for (int i = L; i < nb; i += 32) M.psib[m * nb + i] = psib_s[i];
           if (M.bgrid)
-            for (int i = L; i < nb; i += 32) M.bgrid[m * nb + i] = G.at(i);
+            for (int i = L; i < nb; i += 32) M.bgrid[m * nb + i] = BG.at(i);
         }
         rt::syncwarp();
       }
     }
     if (SO) {
       double ek[LPL], gm[LPL], ysv[LPL];
-      pm::so_solve<LPL>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ny, so, zs, nz, &status);
+      pm::so_solve<LPL>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so, zs, nz, &status);
       if (write) {
         pm::store_lev<LPL>(psi_so, M.Psi_so + m * nz, nz);
         if (M.Psi_Ek) pm::store_lev<LPL>(ek, M.Psi_Ek + m * nz, nz);
@@ -88,11 +98,11 @@ PM_GLOBAL void k_model(RunArgs a) {
       const double south_leg = SO ? psi_so[j] : 0.0;
       wA[j] = (north_leg - south_leg) * 1e6;
     }
-    col_refold<LPL>(cb, M.basin, m, wA, zs, nz, dt);
+    pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
     if (NORTH) {
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) wA[j] = -iso_n[j] * 1e6;
-      col_refold<LPL>(cn, M.north, m, wA, zs, nz, dt);
+      pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
     }
   };
 
@@ -109,31 +119,36 @@ PM_GLOBAL void k_model(RunArgs a) {
     if (SO) pm::load_lev<LPL>(t2, M.Psi_so + m * nz, nz, 0.0);
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? t1[j] : 0.0) - (SO ? t2[j] : 0.0)) * 1e6;
-    col_refold<LPL>(cb, M.basin, m, wA, zs, nz, dt);
+    pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
     if (NORTH) {
       pm::load_lev<LPL>(t1, M.Psi_iso_n + m * nz, nz, 0.0);
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) wA[j] = -t1[j] * 1e6;
-      col_refold<LPL>(cn, M.north, m, wA, zs, nz, dt);
+      pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
     }
   }
-  // surface condition of non-convecting columns (column.py:230-231); p = q = 0 keeps it
+  // boundary values of "plain" columns are invariant under the step: set them once
+  // (surface: column.py:230-231, bottom: column.py:232)
   if (!cb.conv) pm::set_level<LPL>(cb.b, nz - 1, cb.bs);
-  if (NORTH && !cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
+  if (cb.plain) col_bottom<LPL>(cb, zs);
+  if (NORTH) {
+    if (!cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
+    if (cn.plain) col_bottom<LPL>(cn, zs);
+  }
 
   const long long K = M.K, it_end = a.it0 + a.nsteps;
   // last iteration of this launch that re-diagnoses: only that one writes diagnostics to HBM
   const long long last_refresh = ((it_end - 1) / K) * K;
   long long ii = a.it0;
   while (ii < it_end) {
-    // iterations up to and including the next multiple of K
-    long long stop = ((ii + K - 1) / K) * K;  // next ii' >= ii with ii' % K == 0
+    const long long stop = ((ii + K - 1) / K) * K;  // next iteration with it % K == 0
     const bool hits = stop < it_end;
-    const long long upto = hits ? stop + 1 : it_end;
-    for (; ii < upto; ++ii) {
-      col_advance<LPL>(cb, zs, nz);
-      if (NORTH) col_advance<LPL>(cn, zs, nz);
+    const int n = (int)((hits ? stop + 1 : it_end) - ii);
+    for (int s = 0; s < n; ++s) {
+      col_advance<LPL>(cb, G, nz);
+      if (NORTH) col_advance<LPL>(cn, G, nz);
     }
+    ii += n;
     if (hits) refresh(stop == last_refresh);
   }
 

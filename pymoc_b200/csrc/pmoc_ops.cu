@@ -19,21 +19,26 @@ struct ColumnArgs {
 template <int LPL>
 PM_GLOBAL void k_column(ColumnArgs a) {
   const int nz = a.nz, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
-  double* zs = rt::smem();
-  for (int i = W * 32 + L; i < 32 * LPL + 4; i += nthr) zs[i] = a.z[i < nz ? i : nz - 1];
+  const SmemPlan sp = plan_smem(LPL, 0, 2, 0);
+  double* sm = rt::smem();
+  pm::geo_fill<LPL>(sm + sp.off_zs, sm + sp.off_zl, sm + sp.off_rdu, sm + sp.off_rdd, sm + sp.off_ruu,
+                    sm + sp.off_rdd2, a.z, nz, W * 32 + L, nthr);
   rt::syncblock();
+  const pm::GeoTab G = geo_of(sm, sp);
   const long long m = rt::block_idx() * rt::warps_per_block() + W;
   if (m >= a.M) return;
   ColRegs<LPL> c;
   col_load<LPL>(c, a.col, m, nz);
-  if (a.stages & PMOC_STAGE_CONVECT) pm::col_convect<LPL>(c.b, c.bs, c.N2min, zs, nz);
+  c.tab = coltab_of(sm + sp.off_warp0 + (size_t)sp.per_warp * W, sp, 0);
+  if (a.stages & PMOC_STAGE_CONVECT) pm::col_convect<LPL>(c.b, c.bs, c.N2min, G.zs, G.zl, nz);
   if (a.stages & PMOC_STAGE_VERTADVDIFF) {
     double wA[LPL];
     pm::load_lev<LPL>(wA, vrow(a.wA, m), nz, 0.0);
-    col_refold<LPL>(c, a.col, m, wA, zs, nz, a.dt);
-    if (!c.conv) pm::set_level<LPL>(c.b, nz - 1, c.bs);
-    c.conv = false;  // the convect stage (if any) already ran
-    col_advance<LPL>(c, zs, nz);
+    col_retabulate<LPL>(c, a.col, m, G, nz, a.dt);
+    pm::col_coeffs<LPL>(c.p, c.q, wA, c.tab, G, nz);
+    if (!c.conv) pm::set_level<LPL>(c.b, nz - 1, c.bs);  // column.py:230-231
+    col_bottom<LPL>(c, G.zs);
+    pm::col_step<LPL>(c.b, c.p, c.q);
   }
   if (a.stages & PMOC_STAGE_HORADV)
     pm::col_horadv<LPL>(c.b, vrow(a.vdx_in, m), vrow(a.b_in, m), vrow(a.col.Area, m), nz, a.dt);
@@ -107,7 +112,8 @@ PM_GLOBAL void k_so(SoArgs a) {
   const int nz = M.nz, ny = M.ny, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
   double* zs = rt::smem();
   double* ysm = zs + a.nzp + 4;
-  double* bss = ysm + a.nyp + (size_t)a.nyp * W;
+  double* bss = ysm + a.nyp + (size_t)2 * a.nyp * W;
+  double* sinv = bss + a.nyp;
   for (int i = W * 32 + L; i < a.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
   for (int i = W * 32 + L; i < a.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
   rt::syncblock();
@@ -124,7 +130,8 @@ PM_GLOBAL void k_so(SoArgs a) {
   double b[LPL], psi[LPL], ek[LPL], gm[LPL], ysv[LPL];
   pm::load_lev<LPL>(b, vrow(a.b, m), nz, 0.0);
   unsigned status = 0;
-  pm::so_solve<LPL>(psi, ek, gm, ysv, b, ysm, bss, ny, so, zs, nz, &status);
+  const pm::SoSurf surf = pm::so_scan(ysm, bss, sinv, ny);
+  pm::so_solve<LPL>(psi, ek, gm, ysv, b, ysm, bss, sinv, ny, surf, so, zs, nz, &status);
   pm::store_lev<LPL>(psi, a.Psi + m * nz, nz);
   if (a.Psi_Ek) pm::store_lev<LPL>(ek, a.Psi_Ek + m * nz, nz);
   if (a.Psi_GM) pm::store_lev<LPL>(gm, a.Psi_GM + m * nz, nz);
@@ -243,7 +250,7 @@ int pmoc_column_timestep(int64_t M, int32_t nz, const double* z, const pmoc_colu
   if ((stages & PMOC_STAGE_HORADV) && (!vdx_in.ptr || !b_in.ptr)) return fail(PMOC_EINVAL, "vdx_in / b_in missing");
   ColumnArgs a{M, nz, z, *col, wA, vdx_in, b_in, dt, stages};
   PM_DISPATCH_LPL(nz, return launch(k_column<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
-                                    sizeof(double) * (32 * LPL + 4), stream, a));
+                                    plan_smem(LPL, 0, 2, 0).bytes(kWarpsPerBlock), stream, a));
   return PMOC_OK;
 }
 
@@ -287,7 +294,7 @@ int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, do
   PM_DISPATCH_LPL(so->nz, {
     a.nzp = 32 * LPL;
     return launch(k_so<LPL>, blocks_for(so->M), 32 * kWarpsPerBlock,
-                  sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + a.nyp * kWarpsPerBlock), stream, a);
+                  sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + 2 * a.nyp * kWarpsPerBlock), stream, a);
   });
   return PMOC_OK;
 }

@@ -1,0 +1,178 @@
+"""Checks of the drop-in classes, shared by the emulator (CPU) and CUDA (GPU) test files.
+
+They mirror the reference's own unit tests (tests/modules/test_column.py etc.) and add the
+bit-level fixtures of tests/golden/units.npz produced by the reference itself.
+"""
+import numpy as np
+import pytest
+
+from helpers import golden, relmax
+from pymoc_b200.modules import Column, Psi_SO, Psi_Thermwind
+
+TOL = 1e-10
+
+
+# ------------------------------------------------------------------------------- Column
+def column_init_errors():
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  with pytest.raises(TypeError) as e:
+    Column(z=z, kappa=2e-5, Area=None)
+  assert str(e.value) == "('Area', 'needs to be either function, numpy array, or float')"
+  with pytest.raises(TypeError) as e:
+    Column(z=z, kappa=None, Area=6e13)
+  assert str(e.value) == "('kappa', 'needs to be either function, numpy array, or float')"
+  for bad in (None, 50, np.array([])):
+    with pytest.raises(TypeError) as e:
+      Column(z=bad, kappa=2e-5, Area=6e13)
+    assert str(e.value) == 'z needs to be numpy array providing grid levels'
+  col = Column(z=z, kappa=2e-5, Area=6e13)
+  assert (col.bs, col.bbot, col.bzbot, col.N2min) == (0.025, 0.0, None, 1e-7)
+  assert np.array_equal(col.b, 0. * z)
+  arr = np.linspace(0.03, -0.001, 80)
+  assert Column(z=z, kappa=2e-5, Area=6e13, b=arr).b is arr  # aliasing, make_array.py:30-31
+
+
+def column_reference_tests():
+  # tests/modules/test_column.py:272-282 (exact)
+  N2min = 1.5e-7
+  z = np.asarray([-4000.0, -1000.0, -100.0, 0.0])
+  b = np.asarray([-0.03, -0.02, 0.01, 0.01])
+  col = Column(z=z, b=b.copy(), bs=0.0, N2min=N2min, kappa=2e-5, Area=6e13)
+  b[2:] = 0.0 + N2min * (z[2:] - z[1])
+  col.convect()
+  assert all(col.b == b)
+  # test_column.py:247-270 (3 decimals)
+  dt, Area = 60 * 86400, 6e13
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  b = np.linspace(0.03, -0.002, 80)
+  wA = Area * np.sin(z)
+  db_dt1 = (0.0004 / 50.0 / Area) * (-wA)
+  col = Column(z=z, Area=Area, kappa=2e-5, b=b.copy(), bbot=-0.002, bs=0.03)
+  col.vertadvdiff(wA, dt, do_conv=False)
+  assert all(np.around(col.b[2:-2], decimals=3) == np.around(b[2:-2] - dt * db_dt1[2:-2], decimals=3))
+  # test_column.py:284-296 (4 decimals)
+  z = np.asarray([-4000.0, -1000.0, -100.0, 0.0])
+  b = np.asarray([-0.03, 0.01, -0.0025, -0.002])
+  col = Column(z=z, b=b.copy(), kappa=2e-5, Area=6e13)
+  b[0] = -0.03 + dt * 2e6 / 6e13
+  col.horadv(np.asarray([2e8, 2.5e8, 0.0, 0.0]), np.asarray([-0.02, 0.01, -0.001, 0.001]), dt)
+  assert all(np.around(col.b, decimals=4) == np.around(b, decimals=4))
+  # test_column.py:298-336: order convect -> vertadvdiff -> horadv, exact composition
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  b = np.linspace(-np.sqrt(0.04), 0.0, 80)**2.
+  vdx_in = np.asarray([2e4 for n in z])
+  b_in = np.asarray([-0.02 for n in z])
+  wA = np.sin(z) / Area
+  dt = 30 * 86400
+  mk = lambda: Column(z=z, b=b.copy(), bs=-0.0, bbot=-0.04, kappa=2e-5, Area=Area)
+  c1, c2 = mk(), mk()
+  c1.timestep(wA=wA, dt=dt)
+  c2.vertadvdiff(wA=wA, dt=dt)
+  assert all(c1.b == c2.b)
+  c2.horadv(vdx_in=vdx_in, b_in=b_in, dt=dt)
+  c2.convect()
+  assert any(c1.b != c2.b)
+  c1, c2 = mk(), mk()
+  c1.timestep(wA=wA, dt=dt, b_in=b_in, vdx_in=vdx_in)
+  c2.vertadvdiff(wA=wA, dt=dt)
+  c2.horadv(vdx_in=vdx_in, b_in=b_in, dt=dt)
+  assert all(c1.b == c2.b)
+  c1, c2 = mk(), mk()
+  c1.timestep(wA=wA, dt=dt, b_in=b_in, vdx_in=vdx_in, do_conv=True)
+  c2.convect()
+  c2.vertadvdiff(wA=wA, dt=dt)
+  c2.horadv(vdx_in=vdx_in, b_in=b_in, dt=dt)
+  assert all(c1.b == c2.b)
+  with pytest.raises(TypeError) as e:
+    mk().timestep(wA=wA, dt=dt, vdx_in=vdx_in)
+  assert str(e.value) == 'b_in is needed if vdx_in is provided'
+
+
+def column_golden_units():
+  for i, d in golden('units')['column'].items():
+    inp, out = d['inp'], d['out']
+    mk = lambda: Column(z=inp['z'], kappa=inp['kappa'], Area=inp['Area'], b=inp['b'].copy(), bs=inp['bs'],
+                        bbot=inp['bbot'], bzbot=inp['bzbot'], N2min=inp['N2min'])
+    for tag, kw in (('plain', {}), ('conv', dict(do_conv=True)),
+                    ('conv_hor', dict(do_conv=True, vdx_in=inp['vdx_in'], b_in=inp['b_in'])),
+                    ('hor', dict(vdx_in=inp['vdx_in'], b_in=inp['b_in']))):
+      col = mk()
+      for s in range(3):
+        col.timestep(wA=inp['wA'], dt=inp['dt'], **kw)
+        assert relmax(col.b, out[tag][s]) < TOL, (i, tag, s, relmax(col.b, out[tag][s]))
+    col = mk()
+    col.convect()
+    assert np.array_equal(col.b, out['convect_only']), i  # un-fused arithmetic: bit exact
+    assert np.array_equal(col.dAkappa_dz(inp['z']), out['dAkappa_dz'])
+
+
+# ------------------------------------------------------------------------ Psi_Thermwind
+def thermwind_checks():
+  with pytest.raises(TypeError) as e:
+    Psi_Thermwind(z=1.0, b1=0.1)
+  assert str(e.value) == 'z needs to be numpy array providing grid levels'
+  for i, d in golden('units')['thermwind'].items():
+    inp, out = d['inp'], d['out']
+    if inp['z'].size > 256:
+      continue
+    tw = Psi_Thermwind(z=inp['z'], b1=inp['b1'].copy(), b2=inp['b2'].copy(), f=inp['f'])
+    tw.solve()
+    assert relmax(tw.Psi, out['Psi']) < TOL, (i, relmax(tw.Psi, out['Psi']))
+    if 'psib' in out:
+      tw.Psi = out['Psi'].copy()  # isolate the remap
+      with np.errstate(all='ignore'):
+        psib = tw.Psib(500)
+        assert relmax(tw.bgrid, out['bgrid']) == 0.0, i
+        assert relmax(psib, out['psib']) < TOL, (i, relmax(psib, out['psib']))
+        iso = tw.Psibz(500)
+        assert relmax(iso[0], out['iso_b']) < TOL and relmax(iso[1], out['iso_n']) < TOL, i
+        assert relmax(tw.Psib(37), out['psib37']) < TOL, i
+  # callable profiles (first Psi of example_timestepping.py): the kernel gets mid-point samples, i.e. what
+  # solve_bvp's collocation sees on the un-refined mesh.  For this curved profile solve_bvp inserts a
+  # node (70 -> 71, rms residual 3e-4 after) and is therefore adaptive; stated tolerance 1e-6 (measured 2.5e-8).
+  z = np.asarray(np.linspace(-3500, 0, 70))
+  f_b = lambda zz: 0.03 * np.exp(zz / 300.) - 0.0004
+  tw = Psi_Thermwind(z=z, b1=f_b)
+  tw.solve()
+  from scipy import integrate
+  ref = integrate.solve_bvp(lambda x, y: np.vstack((y[1], 1. / 1.2e-4 * (0. + 0 * x - f_b(x)))),
+                            lambda ya, yb: np.array([ya[0], yb[0]]), z, np.zeros((2, 70))).sol(z)[0, :] / 1e6
+  assert relmax(tw.Psi, ref) < 1e-6, relmax(tw.Psi, ref)
+
+
+# ------------------------------------------------------------------------------- Psi_SO
+def so_checks():
+  z = np.asarray(np.linspace(-4000, 0, 81))
+  y = np.asarray(np.linspace(0, 2.0e6, 51))
+  with pytest.raises(TypeError) as e:
+    Psi_SO(z=-2000)
+  assert str(e.value) == 'z needs to be numpy array providing grid levels'
+  with pytest.raises(TypeError) as e:
+    Psi_SO(z=z, y=1e6)
+  assert str(e.value) == 'y needs to be numpy array providing horizontal grid (or boundaries) of ACC'
+  so = Psi_SO(z=z, y=y, b=np.linspace(0.03, -0.001, 81), bs=np.linspace(0.05, 0.10, 51), tau=0.12)
+  # tests/modules/test_psi_SO.py:120-133
+  assert np.round(so.ys(0.02), decimals=3) == np.round(y[0] - 1e3, decimals=3)
+  assert np.round(so.ys(0.2), decimals=3) == np.round(y[-1], decimals=3)
+  for i in range(len(y)):
+    assert np.round(so.ys(so.bs(y[i])), decimals=3) == np.round(y[i], decimals=3)
+  # test_psi_SO.py:144-155 constant wind stress
+  ekman = [(so.L * 0.12) / (so.f * so.rho)] * len(z)
+  ekman[-1] = 0
+  assert all(np.around(ekman, decimals=3) == np.around(so.calc_Ekman(), decimals=3))
+  # test_psi_SO.py:371-412
+  so.solve()
+  assert so.Psi[0] == 0.0
+  assert np.array_equal(so.Psi[1:], (so.Psi_Ek + so.Psi_GM)[1:])
+  for i, d in golden('units')['so'].items():
+    inp, out = d['inp'], d['out']
+    if inp['c'] is not None or isinstance(inp['tau'], np.ndarray):
+      continue  # F2010 smoother / tau(y): see test_so_extensions
+    kw = {k: inp[k] for k in ('f', 'rho', 'L', 'KGM', 'Hsill', 'HEk', 'Htapertop', 'Htaperbot', 'smax')}
+    so = Psi_SO(z=inp['z'], y=inp['y'], b=inp['b'].copy(), bs=inp['bs'].copy(), tau=inp['tau'], **kw)
+    so.solve()
+    for got, key in ((so.Psi, 'Psi'), (so.Psi_Ek, 'Psi_Ek'), (so.Psi_GM, 'Psi_GM')):
+      assert relmax(got, out[key]) < TOL, (i, key, relmax(got, out[key]))
+    assert np.array_equal(so.Psi_Ek, out['Psi_Ek']), i  # same operations in the same order: bit exact
+    ys = np.array([so.ys(v) for v in inp['b'][::8]])
+    assert np.abs(ys - out['ys'][::8]).max() < 1e-6, i  # metres; brentq's own tolerance is ~4e-9 m
