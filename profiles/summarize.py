@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Turn Nsight Compute output into the short text summaries committed under profiles/.
+
+    python profiles/summarize.py launches <launch-list.csv>          # --metrics gpu__time_duration.sum pass
+    python profiles/summarize.py full <report.ncu-rep> [kernel-substr]   # --set full capture
+
+The launch list gives each kernel's share of the profiled command; the full capture gives
+the counters quoted in DESIGN.md / bench.py (FP64 pipe utilisation, DRAM bytes, occupancy,
+stall reasons).
+"""
+import csv
+import io
+import subprocess
+import sys
+from collections import OrderedDict
+
+KEEP = (
+    'gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes_read.sum.per_second',
+    'dram__bytes_write.sum.per_second', 'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+    'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+    'smsp__issue_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+    'sm__warps_active.avg.per_cycle_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+    'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+    'launch__occupancy_limit_warps', 'launch__shared_mem_per_block_dynamic', 'launch__grid_size', 'launch__block_size',
+    'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores',
+    'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__cycles_active.avg',
+    'sm__cycles_elapsed.max', 'gpc__cycles_elapsed.max', 'lts__t_sector_hit_rate.pct',
+)
+STALL = 'smsp__average_warps_issue_stalled_'
+
+
+def launches(path):
+  rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+  hdr, rows = rows[0], rows[1:]
+  k, v = hdr.index('Kernel Name'), hdr.index('Metric Value')
+  agg = OrderedDict()
+  for r in rows:
+    name = r[k].split('(')[0][:90]
+    n, t = agg.get(name, (0, 0.0))
+    agg[name] = (n + 1, t + float(r[v].replace(',', '')))
+  total = sum(t for _, t in agg.values())
+  print('launch list: %s  (%d launches, %.3f ms GPU time in total)' % (path, len(rows), total / 1e6))
+  print('%-92s %6s %12s %7s' % ('kernel', 'count', 'total us', 'share'))
+  for name, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print('%-92s %6d %12.1f %6.1f%%' % (name, n, t / 1e3, 100 * t / total))
+
+
+def full(path, substr=''):
+  out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+  rows = list(csv.reader(io.StringIO(out)))
+  hdr, units, rows = rows[0], rows[1], rows[2:]
+  for r in rows:
+    d = dict(zip(hdr, r))
+    if substr and substr not in d['Kernel Name']:
+      continue
+    print('kernel: %s   grid %s x block %s' % (d['Kernel Name'], d.get('Grid Size'), d.get('Block Size')))
+    for key in KEEP:
+      if key in d:
+        print('  %-70s %16s %s' % (key, d[key], units[hdr.index(key)]))
+    stalls = sorted(((float(d[h]), h[len(STALL):].replace('_per_issue_active.ratio', '')) for h in hdr
+                     if h.startswith(STALL) and h.endswith('_per_issue_active.ratio') and d[h]), reverse=True)
+    print('  warp stall reasons (warps stalled per issue-active cycle):')
+    for val, name in stalls[:8]:
+      print('    %-40s %8.3f' % (name, val))
+
+
+if __name__ == '__main__':
+  if sys.argv[1] == 'launches':
+    launches(sys.argv[2])
+  else:
+    full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else '')
