@@ -43,6 +43,7 @@ WORKLOADS = {
     'C2': (lambda M: configs.c2_column_so(M), 65536, 7200),
     'twocol': (lambda M: configs.twocol(M), 32768, 2400),
     'C3': (lambda M: configs.c3_twocol_so(M), 32768, 2400),
+    'C4': (lambda M: configs.c4_jansen_nadeau(M), 32768, 2400),
 }
 
 

@@ -27,6 +27,7 @@ extern "C" {
 
 #define PMOC_ABI_VERSION 1
 #define PMOC_MAX_NZ_WARP 256 /* one warp per member up to this many levels */
+#define PMOC_MAX_NY_ML 64    /* SO_ML surface points per member */
 
 typedef enum {
   PMOC_OK = 0,
@@ -45,7 +46,10 @@ typedef struct {
 #define PMOC_ST_NAN 1u            /* non-finite buoyancy at the end of the launch */
 #define PMOC_ST_BS_NONMONOTONE 2u /* bs(y) not monotone north of argmin: Brent path taken */
 #define PMOC_ST_BRENT_SIGN 4u     /* f(a), f(b) same sign: scipy.optimize.brentq would raise ValueError */
-#define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML */
+#define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML:
+                                     numpy's guess-carrying search is followed query by query */
+#define PMOC_ST_ML_INDEX 16u      /* SO_ML needed np.argwhere(Psi_b > 0)[0][0] / np.nonzero(Psi_b)[0][0] of an
+                                     all-non-positive / all-zero Psi_b: the reference raises IndexError */
 
 /* ---- one advective-diffusive column: reference class Column, column.py:19-72 ------------ */
 typedef struct {

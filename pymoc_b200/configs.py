@@ -164,7 +164,9 @@ def c4_jansen_nadeau(M=1, axes=None):
   """examples/run_JansenNadeau_2018.py:33-261 (default flags) -- two convecting columns,
   thermal wind with isopycnal remap, explicit Psi_SO, SO_ML, bottom-boundary switches.
 
-  Lattice: tau x kapfac x db x B x KGM.
+  Lattice: tau x kapfac x db x B x KGM.  The db axis stops at +0.002:
+  beyond it the reference itself goes NaN in the northern column for kapfac < 0.8 (its explicit
+  upwind step violates the advective CFL there).
   """
   if M == 1:
     sweep = lattice(tau=[0.12], kapfac=[1.0], db=[0.0], B=[5.9e3], KGM=[800.])
@@ -172,7 +174,7 @@ def c4_jansen_nadeau(M=1, axes=None):
     n = axes if axes is not None else _sizes(M, 5)
     sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
                     kapfac=np.geomspace(0.5, 2., n[1]) if n[1] > 1 else [1.0],
-                    db=np.linspace(-0.004, 0.004, n[2]) if n[2] > 1 else [0.0],
+                    db=np.linspace(-0.004, 0.002, n[2]) if n[2] > 1 else [0.0],
                     B=np.linspace(3e3, 9e3, n[3]) if n[3] > 1 else [5.9e3],
                     KGM=np.linspace(500., 1500., n[4]) if n[4] > 1 else [800.])
   assert sweep['tau'].size == M

@@ -41,24 +41,37 @@ constexpr int kWarpsPerBlock = 4;
 struct SmemPlan {
   int nzp, nyp, nbp;
   int off_zs, off_zl, off_rdu, off_rdd, off_ruu, off_rdd2, off_y;  // per block
+  int off_dzu, off_rdzu, off_dzc, off_rdzc;                        // per block, bit-faithful step only
   int off_warp0, per_warp;                                          // per warp region
-  int w_col[2];                                                     // ColTab of basin / north (4*nzp each)
+  int w_col[2];                                                     // column tables of basin / north (4*nzp each)
   int w_ctop, w_crinv, w_cu, w_psib, w_bs, w_sinv;
+  int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
 
+// Topologies with a mixed layer run the bit-faithful column step (pm::col_step_exact): their
+// block tables are dz / 1/dz instead of the folded reciprocals, and the remap scratch psib[nb]
+// overlays per-step arrays that are dead while the streamfunctions are being re-diagnosed.
 static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   SmemPlan s{};
+  const bool exact = (flags & PMOC_HAS_ML) != 0;
   s.nzp = 32 * LPL;
   s.nyp = (ny + 3) & ~3;
   s.nbp = (nb + 3) & ~3;
   int o = 0;
   s.off_zs = o; o += s.nzp + 4;
   s.off_zl = o; o += s.nzp;
-  s.off_rdu = o; o += s.nzp;
-  s.off_rdd = o; o += s.nzp;
-  s.off_ruu = o; o += s.nzp;
-  s.off_rdd2 = o; o += s.nzp;
+  if (!exact) {
+    s.off_rdu = o; o += s.nzp;
+    s.off_rdd = o; o += s.nzp;
+    s.off_ruu = o; o += s.nzp;
+    s.off_rdd2 = o; o += s.nzp;
+  } else {
+    s.off_dzu = o; o += s.nzp;
+    s.off_rdzu = o; o += s.nzp;
+    s.off_dzc = o; o += s.nzp;
+    s.off_rdzc = o; o += s.nzp;
+  }
   s.off_y = o; o += s.nyp;
   s.off_warp0 = o;
   int w = 0;
@@ -68,11 +81,21 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     s.w_ctop = w; w += s.nzp;
     s.w_crinv = w; w += s.nzp;
     s.w_cu = w; w += s.nzp;
-    s.w_psib = w; w += s.nbp;
+    if (!exact) { s.w_psib = w; w += s.nbp; }
   }
   if (flags & PMOC_HAS_SO) {
     s.w_bs = w; w += s.nyp;
     s.w_sinv = w; w += s.nyp;
+  }
+  if (exact) {
+    const int r0 = w;
+    s.w_psib = w;  // live only inside a refresh
+    s.w_nweff[0] = w; w += 2 * s.nzp;
+    s.w_nweff[1] = w; w += 2 * s.nzp;
+    s.w_bb = w; w += s.nzp;
+    s.w_pm = w; w += s.nzp;
+    if (w - r0 < s.nbp) w = r0 + s.nbp;
+    s.w_scan = w; w += 10 * 32;
   }
   s.per_warp = w;
   return s;
@@ -85,6 +108,14 @@ PM_DEV pm::GeoTab geo_of(double* sm, const SmemPlan& sp) {
 PM_DEV pm::ColTab coltab_of(double* ws, const SmemPlan& sp, int which) {
   double* t = ws + sp.w_col[which];
   return pm::ColTab{t, t + sp.nzp, t + 2 * sp.nzp, t + 3 * sp.nzp};
+}
+PM_DEV pm::ExactGeo exactgeo_of(double* sm, const SmemPlan& sp) {
+  return pm::ExactGeo{sm + sp.off_dzu, sm + sp.off_rdzu, sm + sp.off_dzc, sm + sp.off_rdzc};
+}
+PM_DEV pm::ExactCol exactcol_of(double* ws, const SmemPlan& sp, int which) {
+  double* t = ws + sp.w_col[which];
+  double* n = ws + sp.w_nweff[which];
+  return pm::ExactCol{{t, t + sp.nzp}, t + 2 * sp.nzp, t + 3 * sp.nzp, {n, n + sp.nzp}};
 }
 
 struct RunArgs {
@@ -146,6 +177,18 @@ PM_DEV void col_advance(ColRegs<LPL>& c, const pm::GeoTab& G, int nz) {
     col_bottom<LPL>(c, G.zs);
   }
   pm::col_step<LPL>(c.b, c.p, c.q);
+}
+
+// the same for the bit-faithful step (always convecting columns of the 'jn' order)
+template <int LPL>
+PM_DEV void col_advance_exact(ColRegs<LPL>& c, const pm::ExactCol& X, const pm::ExactGeo& EG, const pm::GeoTab& G,
+                              int nz, double dt) {
+  if (c.conv)
+    pm::col_convect<LPL>(c.b, c.bs, c.N2min, G.zs, G.zl, nz);
+  else
+    pm::set_level<LPL>(c.b, nz - 1, c.bs);
+  col_bottom<LPL>(c, G.zs);
+  pm::col_step_exact<LPL>(c.b, X, c.var, EG, nz, dt);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -82,9 +82,16 @@ struct ColTab {
 // block-cooperative fill of the geometry tables (call before the block barrier)
 template <int LPL>
 PM_DEV void geo_fill(double* zs, double* zl, double* rdu, double* rdd, double* ruu, double* rdd2,
-                     const double* PM_RESTRICT z, int nz, int tid, int nthr) {
+                     const double* PM_RESTRICT z, int nz, int tid, int nthr, bool folded = true) {
   const int nzp = 32 * LPL;
   for (int i = tid; i < nzp + 4; i += nthr) zs[i] = z[i < nz ? i : nz - 1];
+  if (!folded) {
+    for (int s = tid; s < nzp; s += nthr) {
+      const int i = (s & 31) * LPL + (s >> 5);
+      zl[s] = z[i < nz ? i : nz - 1];
+    }
+    return;
+  }
   for (int s = tid; s < nzp; s += nthr) {
     const int L = s & 31, j = s >> 5, i = L * LPL + j;
     double a = 0., b = 0., c = 0., d = 0.;
@@ -159,6 +166,92 @@ PM_DEV void col_step(double (&b)[LPL], const double (&p)[LPL], const double (&q)
     const double d = (j < LPL - 1 ? b[j + 1 < LPL ? j + 1 : j] : bnext) - b[j];
     b[j] = rt::fma(-q[j], dm, rt::fma(p[j], d, b[j]));
     dm = d;
+  }
+}
+
+// ---- bit-faithful step ---------------------------------------------------------------------
+// The same IEEE operations in the same order as column.py:235-249, with every divide by a
+// state-independent number c done as div_const(x, c, 1/c) (correctly rounded, 3 FMAs).  Used
+// where the loop sits on structural ties that the folded form would break: in the 'jn' order
+// the no-flux bottom condition bbot = b[1] converges to b[0] == b[1] *exactly*, and a one-ulp
+// difference flips a flat remap cell into an inverted one (Psib is discontinuous there).
+struct ExactGeo {
+  const double *dzu, *rdzu, *dzc, *rdzc;  // lane-major, nzp each: cell above each level, centred spacing
+};
+struct ExactCol {
+  double *kap[2], *area, *rarea, *nweff[2];  // lane-major, nzp each (per warp); [variant]
+};
+
+template <int LPL>
+PM_DEV void geo_fill_exact(double* dzu, double* rdzu, double* dzc, double* rdzc, const double* PM_RESTRICT z, int nz,
+                           int tid, int nthr) {
+  const int nzp = 32 * LPL;
+  for (int s = tid; s < nzp; s += nthr) {
+    const int L = s & 31, j = s >> 5, i = L * LPL + j;
+    double a = 1., c = 1.;
+    if (i < nz - 1) a = z[i + 1] - z[i];
+    if (i >= 1 && i < nz - 1) c = 0.5 * ((z[i + 1] - z[i]) + (z[i] - z[i - 1]));
+    dzu[s] = a;
+    rdzu[s] = 1. / a;
+    dzc[s] = c;
+    rdzc[s] = 1. / c;
+  }
+}
+
+template <int LPL>
+PM_DEV void col_tabulate_exact(const ExactCol& T, const double* PM_RESTRICT kappa, const double* PM_RESTRICT Area,
+                               int nz, int nvar) {
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j), s = lm(j);
+    const bool in = i >= 1 && i < nz - 1;
+    const double A = in ? Area[i] : 1.0;
+    T.area[s] = A;
+    T.rarea[s] = 1.0 / A;
+    T.kap[0][s] = in ? kappa[i] : 0.0;
+    T.kap[1][s] = in ? kappa[(nvar > 1 ? nz : 0) + i] : 0.0;
+  }
+  rt::syncwarp();
+}
+
+// -weff = -(wA - d(A kappa)/dz) for both kappa variants (column.py:241,245)
+template <int LPL>
+PM_DEV void col_nweff(const ExactCol& T, const double (&wA)[LPL], const double* PM_RESTRICT dAk, int nz, int nvar) {
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j), s = lm(j);
+    const bool in = i >= 1 && i < nz - 1;
+    T.nweff[0][s] = in ? -(wA[j] - dAk[i]) : 0.0;
+    T.nweff[1][s] = in ? -(wA[j] - dAk[(nvar > 1 ? nz : 0) + i]) : 0.0;
+  }
+  rt::syncwarp();
+}
+
+template <int LPL>
+PM_DEV void col_step_exact(double (&b)[LPL], const ExactCol& T, int var, const ExactGeo& G, int nz, double dt) {
+  const double* kap = T.kap[var];
+  const double* nweff = T.nweff[var];
+  const double bnext = rt::shfl_down(b[0], 1);
+  double bzu[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int s = lm(j);
+    const double up = j < LPL - 1 ? b[j + 1 < LPL ? j + 1 : j] : bnext;
+    bzu[j] = div_const(up - b[j], G.dzu[s], G.rdzu[s]);
+  }
+  const double bzprev = rt::shfl_up(bzu[LPL - 1], 1);
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j), s = lm(j);
+    if (i >= 1 && i < nz - 1) {
+      const double bzd = j > 0 ? bzu[j > 0 ? j - 1 : 0] : bzprev;
+      const double bzz = div_const(bzu[j] - bzd, G.dzc[s], G.rdzc[s]);
+      const double nw = nweff[s];
+      const double sel = nw > 0 ? bzu[j] : bzd;  // weff < 0  <=>  -weff > 0
+      const double adv = div_const(nw * sel, T.area[s], T.rarea[s]);
+      const double tend = adv + kap[s] * bzz;
+      b[j] = b[j] + dt * tend;
+    }
   }
 }
 
@@ -573,6 +666,320 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     psi[j] = ps;
     ysv[j] = yo;
   }
+}
+
+// ====================================================================== SO_ML
+// Southern-Ocean mixed layer (SO_ML.py:198-303).  The ny <= 64 surface points are spread
+// two per lane (point k lives in lane k/2); everything below is warp-cooperative.
+constexpr int kMLP = 2;
+constexpr int kMaxNyMl = 32 * kMLP;
+
+// numpy/_core/src/multiarray/compiled_base.c: binary_search_with_guess, statement for
+// statement.  For a sorted `arr` the result does not depend on `guess`; for an unsorted
+// one (np.interp with a non-monotone b_basin as abscissa) it does, and the
+// reference's answer is reproduced only by carrying the guess from query to query.
+PM_DEV int search_guess(double key, const double* arr, int len, int guess) {
+  constexpr int kLikelyInCache = 8;
+  int imin = 0, imax = len;
+  if (key > arr[len - 1]) return len;
+  if (key < arr[0]) return -1;
+  if (len <= 4) {
+    int i = 1;
+    for (; i < len && key >= arr[i]; ++i) {}
+    return i - 1;
+  }
+  if (guess > len - 3) guess = len - 3;
+  if (guess < 1) guess = 1;
+  if (key < arr[guess]) {
+    if (key < arr[guess - 1]) {
+      imax = guess - 1;
+      if (guess > kLikelyInCache && key >= arr[guess - kLikelyInCache]) imin = guess - kLikelyInCache;
+    } else {
+      return guess - 1;
+    }
+  } else {
+    if (key < arr[guess + 1]) return guess;
+    if (key < arr[guess + 2]) return guess + 1;
+    imin = guess + 2;
+    if (guess < len - kLikelyInCache - 1 && key < arr[guess + kLikelyInCache]) imax = guess + kLikelyInCache;
+  }
+  while (imin < imax) {
+    const int imid = imin + ((imax - imin) >> 1);
+    if (key >= arr[imid])
+      imin = imid + 1;
+    else
+      imax = imid;
+  }
+  return imin - 1;
+}
+
+// one query of np.interp(x, xp, fp) the way arr_interp evaluates it; *j is the carried guess
+PM_DEV double interp_np(double x, const double* xp, const double* fp, int n, int* j) {
+  if (x != x) return x;
+  const int k = search_guess(x, xp, n, *j);
+  *j = k;
+  if (k == -1) return fp[0];
+  if (k == n) return fp[n - 1];
+  if (k == n - 1) return fp[k];
+  if (xp[k] == x) return fp[k];
+  const double slope = (fp[k + 1] - fp[k]) / (xp[k + 1] - xp[k]);
+  double res = slope * (x - xp[k]) + fp[k];
+  if (res != res) {
+    res = slope * (x - xp[k + 1]) + fp[k + 1];
+    if (res != res && fp[k] == fp[k + 1]) res = fp[k];
+  }
+  return res;
+}
+
+struct MlState {
+  double bs[kMLP];                            // surface buoyancy of the lane's points
+  double ps[kMLP];                            // Psi_s of the last step (diagnostic)
+  double a[kMLP], m[kMLP];                    // Thomas factors of U = tridiag(-s/2, 1+s, -s/2)
+  double sfh[kMLP], rv[kMLP], brest[kMLP];    // surflux/h, rest_mask*v_pist/h, b_rest
+  double shalf, sdiag;                        // s/2, 1-s
+  double h, rh, L, rL, dy, rdy;
+  int ny;
+  int first_pos;                              // np.argwhere(Psi_b > 0)[0][0], -1 if none
+  const double* scan;                         // lane-major [10][32] scan multipliers (shared memory)
+};
+
+PM_DEV int mlk(int e) { return rt::lane() * kMLP + e; }
+
+// State-independent part of SO_ML: flux factors and the factorisation of the Crank-Nicolson
+// matrix (SO_ML.py:155-165, 191-196).  inv(U).V.bs is evaluated as a Thomas solve whose two
+// first-order recurrences run as warp scans; the multipliers of the scan levels are
+// tabulated here (scan_s: 10*32 doubles of shared memory owned by this warp).
+PM_DEV void ml_setup(MlState& S, const double* ygrid, int ny, double Ks, double h, double L, double vpist,
+                     const double* PM_RESTRICT surflux, const double* PM_RESTRICT rest_mask,
+                     const double* PM_RESTRICT b_rest, double dt, double* scan_s) {
+  S.ny = ny;
+  S.h = h; S.rh = 1.0 / h;
+  S.L = L; S.rL = 1.0 / L;
+  S.dy = ygrid[1] - ygrid[0];
+  S.rdy = 1.0 / S.dy;
+  const double s = Ks * dt / (S.dy * S.dy);
+  S.shalf = s / 2.;
+  S.sdiag = 1 - s;
+  S.first_pos = -1;
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    const int k = mlk(e);
+    const bool in = k < ny;
+    S.sfh[e] = in ? surflux[k] / h : 0.0;
+    S.rv[e] = in ? rest_mask[k] * vpist / h : 0.0;
+    S.brest[e] = in ? b_rest[k] : 0.0;
+    S.a[e] = 0.0;
+    S.m[e] = in ? 1.0 : 0.0;  // identity rows (first, last); padding contributes nothing
+    S.ps[e] = 0.0;
+  }
+  double aprev = 0.0;
+  for (int i = 1; i < ny - 1; ++i) {
+    const double mi = 1. / ((1 + s) - S.shalf * aprev);
+    aprev = S.shalf * mi;
+    PM_UNROLL
+    for (int e = 0; e < kMLP; ++e)
+      if (mlk(e) == i) {
+        S.m[e] = mi;
+        S.a[e] = aprev;
+      }
+  }
+  // lane composites: forward y_last = A*y_prev + C, backward x_first = A*x_next + D (same product)
+  const int Ln = rt::lane();
+  double F = S.a[0] * S.a[1], B = F;
+  int lvl = 0;
+  for (int d = 1; d < 32; d <<= 1, ++lvl) {
+    scan_s[lvl * 32 + Ln] = Ln >= d ? F : 0.0;
+    scan_s[(5 + lvl) * 32 + Ln] = Ln + d < 32 ? B : 0.0;
+    const double fo = rt::shfl_up(F, d), bo = rt::shfl_down(B, d);
+    if (Ln >= d) F = F * fo;
+    if (Ln + d < 32) B = B * bo;
+  }
+  S.scan = scan_s;
+  rt::syncwarp();
+}
+
+// (value, index) arg-min with np.argmin's rules: first occurrence, NaN wins.
+PM_DEV int ml_argmin(const MlState& S) {
+  double v = INFINITY;
+  int idx = 0x7fffffff;
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    const int k = mlk(e);
+    if (k < S.ny) {
+      const double x = S.bs[e];
+      const bool better = idx == 0x7fffffff || ((x != x) && (v == v)) || x < v;
+      if (better) { v = x; idx = k; }
+    }
+  }
+  for (int msk = 16; msk > 0; msk >>= 1) {
+    const double ov = rt::shfl_xor(v, msk);
+    const int oi = rt::shfl_i(idx, rt::lane() ^ msk);
+    const bool vnan = v != v, onan = ov != ov;
+    bool take;
+    if (oi == 0x7fffffff) take = false;
+    else if (idx == 0x7fffffff) take = true;
+    else if (vnan || onan) take = onan && (!vnan || oi < idx);
+    else take = ov < v || (ov == v && oi < idx);
+    if (take) { v = ov; idx = oi; }
+  }
+  return idx;
+}
+
+PM_DEV void ml_south_bc(MlState& S, double ps1, const double* bb_s, unsigned* status) {
+  // SO_ML.py:93-98
+  if (rt::lane() == 0) {
+    if (ps1 > 0) {
+      if (S.first_pos >= 0)
+        S.bs[0] = bb_s[S.first_pos];
+      else
+        *status |= 16u;  // the reference raises IndexError here
+    } else {
+      S.bs[0] = S.bs[1];
+    }
+  }
+}
+
+// SO_ML.advdiff (SO_ML.py:228-274) for one step.  bb_s: b_basin, pm_s: Psi_mod (Psi_b with the
+// leading zeros replaced, SO_ML.py:228-230), both natural order in shared memory; bs_s: scratch
+// [ny] of this warp.  `sorted`: b_basin is non-decreasing (warp-uniform).
+PM_DEV void ml_step(MlState& S, const double* bb_s, const double* pm_s, int nz, bool sorted, double* bs_s, double dt,
+                    unsigned* status) {
+  const int ny = S.ny, Ln = rt::lane();
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e)
+    if (mlk(e) < ny) bs_s[mlk(e)] = S.bs[e];
+  rt::syncwarp();
+  double ps[kMLP] = {0., 0.};
+  if (sorted) {
+    PM_UNROLL
+    for (int e = 0; e < kMLP; ++e)
+      if (mlk(e) < ny) ps[e] = interp1(S.bs[e], bb_s, pm_s, nz);
+  } else {
+    *status |= 8u;  // PMOC_ST_XP_NONMONOTONE: the guess-carrying search decides, as in numpy
+    int j = 0;
+    for (int k = 0; k < ny; ++k) {
+      const double v = interp_np(bs_s[k], bb_s, pm_s, nz, &j);
+      PM_UNROLL
+      for (int e = 0; e < kMLP; ++e)
+        if (mlk(e) == k) ps[e] = v;
+    }
+  }
+  const int amin = ml_argmin(S);
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e)
+    if (mlk(e) < amin || mlk(e) == 0) ps[e] = 0.0;
+  const double ps1 = rt::shfl(ps[1], 0);
+  ml_south_bc(S, ps1, bb_s, status);
+  // tendencies (SO_ML.py:124-134, 250-259)
+  double prev[kMLP], next[kMLP];
+  prev[0] = rt::shfl_up(S.bs[1], 1);
+  next[0] = S.bs[1];
+  prev[1] = S.bs[0];
+  next[1] = rt::shfl_down(S.bs[0], 1);
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    const int k = mlk(e);
+    const double flux = S.sfh[e] + S.rv[e] * (S.brest[e] - S.bs[e]);
+    double adv = 0.0;
+    if (k >= 1 && k < ny - 1) {
+      double t = 0.0;
+      bool on = false;
+      if (ps[e] < 0.) {
+        t = -ps[e] * 1e6 * (next[e] - S.bs[e]);
+        on = true;
+      } else if (ps[e] > 0.) {
+        t = -ps[e] * 1e6 * (S.bs[e] - prev[e]);
+        on = true;
+      }
+      if (on) adv = div_const(div_const(div_const(t, S.h, S.rh), S.L, S.rL), S.dy, S.rdy);
+    }
+    if (k < ny) S.bs[e] = S.bs[e] + dt * (flux + adv);
+    S.ps[e] = ps[e];
+  }
+  if (Ln == 0 && ps1 <= 0) S.bs[0] = S.bs[1];
+  // Crank-Nicolson diffusion: rhs = V.bs, then U x = rhs by a scanned Thomas solve
+  prev[0] = rt::shfl_up(S.bs[1], 1);
+  next[0] = S.bs[1];
+  prev[1] = S.bs[0];
+  next[1] = rt::shfl_down(S.bs[0], 1);
+  double c[kMLP];
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    const int k = mlk(e);
+    double r = S.bs[e];
+    if (k >= 1 && k < ny - 1) r = S.shalf * prev[e] + S.sdiag * S.bs[e] + S.shalf * next[e];
+    c[e] = k < ny ? r * S.m[e] : 0.0;
+  }
+  double C = rt::fma(S.a[1], c[0], c[1]);
+  int lvl = 0;
+  for (int d = 1; d < 32; d <<= 1, ++lvl) {
+    const double o = rt::shfl_up(C, d);
+    C = rt::fma(S.scan[lvl * 32 + Ln], Ln >= d ? o : 0.0, C);
+  }
+  double yprev = rt::shfl_up(C, 1);
+  if (Ln == 0) yprev = 0.0;
+  const double dp0 = rt::fma(S.a[0], yprev, c[0]);
+  const double dp1 = rt::fma(S.a[1], dp0, c[1]);
+  double D = rt::fma(S.a[0], dp1, dp0);
+  lvl = 0;
+  for (int d = 1; d < 32; d <<= 1, ++lvl) {
+    const double o = rt::shfl_down(D, d);
+    D = rt::fma(S.scan[(5 + lvl) * 32 + Ln], Ln + d < 32 ? o : 0.0, D);
+  }
+  double xnext = rt::shfl_down(D, 1);
+  if (Ln == 31) xnext = 0.0;
+  const double x1 = rt::fma(S.a[1], xnext, dp1);
+  const double x0 = rt::fma(S.a[0], x1, dp0);
+  if (mlk(0) < ny) S.bs[0] = x0;
+  if (mlk(1) < ny) S.bs[1] = x1;
+  ml_south_bc(S, ps1, bb_s, status);
+}
+
+// Psi_b -> what ml_step needs: Psi_mod in shared memory (natural order) and the first level
+// with Psi_b > 0 (SO_ML.py:94, 228-230).  Returns false when Psi_b has no non-zero entry
+// (np.nonzero(...)[0][0] raises IndexError in the reference).
+template <int LPL>
+PM_DEV bool ml_bind_psi(MlState& S, const double (&psi_b)[LPL], int nz, double* pm_s) {
+  int fnz = 0x7fffffff, fpos = 0x7fffffff;
+  PM_UNROLL
+  for (int j = LPL - 1; j >= 0; --j) {
+    const int i = lev<LPL>(j);
+    if (i < nz) {
+      if (psi_b[j] != 0.0) fnz = i;
+      if (psi_b[j] > 0.0) fpos = i;
+    }
+  }
+  fnz = rt::min_i(fnz);
+  fpos = rt::min_i(fpos);
+  S.first_pos = fpos == 0x7fffffff ? -1 : fpos;
+  const bool ok = fnz != 0x7fffffff;
+  const double held = ok ? get_level<LPL>(psi_b, fnz) : 0.0;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz) pm_s[i] = i < fnz ? held : psi_b[j];
+  }
+  rt::syncwarp();
+  return ok;
+}
+
+// b_basin registers -> shared memory (natural order) + is it non-decreasing?
+template <int LPL>
+PM_DEV bool ml_bind_basin(const double (&b)[LPL], int nz, double* bb_s) {
+  const double bnext = rt::shfl_down(b[0], 1);
+  bool bad = false;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz) bb_s[i] = b[j];
+    if (i < nz - 1) {
+      const double up = j < LPL - 1 ? b[j + 1 < LPL ? j + 1 : j] : bnext;
+      bad |= !(up >= b[j]);
+    }
+  }
+  const bool sorted = rt::ballot(bad) == 0;  // ballot also orders the stores before the reads
+  rt::syncwarp();
+  return sorted;
 }
 
 }  // namespace pm

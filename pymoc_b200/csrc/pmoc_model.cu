@@ -11,6 +11,7 @@ template <int LPL, unsigned TOPO>
 PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
+  constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
   const pmoc_model& M = a.m;
   const SmemPlan& sp = a.sp;
   const int nz = M.nz, ny = M.ny, nb = M.nb;
@@ -19,7 +20,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   double* ysm = sm + sp.off_y;
   double* ws = sm + sp.off_warp0 + (size_t)sp.per_warp * W;
   pm::geo_fill<LPL>(sm + sp.off_zs, sm + sp.off_zl, sm + sp.off_rdu, sm + sp.off_rdd, sm + sp.off_ruu,
-                    sm + sp.off_rdd2, M.z, nz, W * 32 + L, nthr);
+                    sm + sp.off_rdd2, M.z, nz, W * 32 + L, nthr, !ML);
+  if (ML)
+    pm::geo_fill_exact<LPL>(sm + sp.off_dzu, sm + sp.off_rdzu, sm + sp.off_dzc, sm + sp.off_rdzc, M.z, nz, W * 32 + L,
+                            nthr);
   if (SO)
     for (int i = W * 32 + L; i < sp.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
   rt::syncblock();
@@ -30,13 +34,25 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   const double dt = M.dt;
 
   ColRegs<LPL> cb, cn;
+  pm::ExactGeo EG{};
+  pm::ExactCol xb{}, xn{};
   col_load<LPL>(cb, M.basin, m, nz);
-  cb.tab = coltab_of(ws, sp, 0);
-  col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
-  if (NORTH) {
-    col_load<LPL>(cn, M.north, m, nz);
-    cn.tab = coltab_of(ws, sp, 1);
-    col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
+  if (NORTH) col_load<LPL>(cn, M.north, m, nz);
+  if (!ML) {
+    cb.tab = coltab_of(ws, sp, 0);
+    col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
+    if (NORTH) {
+      cn.tab = coltab_of(ws, sp, 1);
+      col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
+    }
+  } else {
+    EG = exactgeo_of(sm, sp);
+    xb = exactcol_of(ws, sp, 0);
+    xn = exactcol_of(ws, sp, 1);
+    pm::col_tabulate_exact<LPL>(xb, vrow(M.basin.kappa, m), vrow(M.basin.Area, m), nz, M.basin.nvar);
+    pm::col_tabulate_exact<LPL>(xn, vrow(M.north.kappa, m), vrow(M.north.Area, m), nz, M.north.nvar);
+    if (M.basin.nvar < 2) cb.var = 0;
+    if (M.north.nvar < 2) cn.var = 0;
   }
   double b2fix[LPL];
   if (TW && !NORTH) pm::load_lev<LPL>(b2fix, vrow(M.tw_b2, m), nz, 0.0);
@@ -49,15 +65,53 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
     so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
     const double* src = vrow(M.so_bs, m);
+    if (ML) src = M.ml_bs + m * ny;  // the mixed layer's bs (run_JansenNadeau_2018.py:214)
     for (int i = L; i < sp.nyp; i += 32) ws[sp.w_bs + i] = src[i < ny ? i : ny - 1];
     rt::syncwarp();
-    surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);  // bs(y) is fixed without a mixed layer
+    if (!ML) surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);  // bs(y) is fixed without a mixed layer
   }
   unsigned status = 0;
+  pm::MlState ml{};
+  double* const bb_s = ws + (ML ? sp.w_bb : 0);
+  double* const pm_s = ws + (ML ? sp.w_pm : 0);
+  double psi_so1 = 0., res_b1 = 0., res_n1 = 0.;  // Psi[1] of the three streamfunctions ('jn' switches)
+  if (ML) {
+    pm::ml_setup(ml, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m),
+                 vrow(M.ml_surflux, m), vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), dt, ws + sp.w_scan);
+    PM_UNROLL
+    for (int e = 0; e < pm::kMLP; ++e) ml.bs[e] = ws[sp.w_bs + (pm::mlk(e) < ny ? pm::mlk(e) : ny - 1)];
+  }
+
+  // Streamfunctions -> stencil coefficients of the columns (and what SO_ML needs).
+  auto apply = [&](const double(&north_leg)[LPL], const double(&iso_n)[LPL], const double(&psi_so)[LPL]) {
+    double wA[LPL];
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? north_leg[j] : 0.0) - (SO ? psi_so[j] : 0.0)) * 1e6;
+    if (ML)
+      pm::col_nweff<LPL>(xb, wA, vrow(M.basin.dAk, m), nz, M.basin.nvar);
+    else
+      pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
+    if (NORTH) {
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = -iso_n[j] * 1e6;
+      if (ML)
+        pm::col_nweff<LPL>(xn, wA, vrow(M.north.dAk, m), nz, M.north.nvar);
+      else
+        pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
+    }
+    if (ML) {
+      psi_so1 = pm::get_level<LPL>(psi_so, 1);
+      res_b1 = pm::get_level<LPL>(north_leg, 1);
+      res_n1 = pm::get_level<LPL>(iso_n, 1);
+      if (!pm::ml_bind_psi<LPL>(ml, psi_so, nz, pm_s)) status |= PMOC_ST_ML_INDEX;
+    }
+  };
 
   // Diagnose the streamfunctions from the current state and fold them into the stencils.
   auto refresh = [&](bool write) {
-    double psi_tw[LPL], iso_b[LPL], iso_n[LPL], psi_so[LPL], wA[LPL];
+    double psi_tw[LPL], iso_b[LPL], iso_n[LPL], psi_so[LPL];
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) psi_tw[j] = iso_b[j] = iso_n[j] = psi_so[j] = 0.0;
     if (TW) {
       const double(&b2)[LPL] = NORTH ? cn.b : b2fix;
       pm::tw_solve<LPL>(psi_tw, cb.b, b2, tw_f, zs, nz, nullptr);
@@ -85,6 +139,13 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     }
     if (SO) {
       double ek[LPL], gm[LPL], ysv[LPL];
+      if (ML) {  // the channel's surface buoyancy is the mixed layer's (run_JansenNadeau_2018.py:214)
+        PM_UNROLL
+        for (int e = 0; e < pm::kMLP; ++e)
+          if (pm::mlk(e) < ny) ws[sp.w_bs + pm::mlk(e)] = ml.bs[e];
+        rt::syncwarp();
+        surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);
+      }
       pm::so_solve<LPL>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so, zs, nz, &status);
       if (write) {
         pm::store_lev<LPL>(psi_so, M.Psi_so + m * nz, nz);
@@ -92,18 +153,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         if (M.Psi_GM) pm::store_lev<LPL>(gm, M.Psi_GM + m * nz, nz);
       }
     }
-    PM_UNROLL
-    for (int j = 0; j < LPL; ++j) {
-      const double north_leg = TW ? (ISO ? iso_b[j] : psi_tw[j]) : 0.0;
-      const double south_leg = SO ? psi_so[j] : 0.0;
-      wA[j] = (north_leg - south_leg) * 1e6;
-    }
-    pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
-    if (NORTH) {
-      PM_UNROLL
-      for (int j = 0; j < LPL; ++j) wA[j] = -iso_n[j] * 1e6;
-      pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
-    }
+    if (ISO)
+      apply(iso_b, iso_n, psi_so);
+    else
+      apply(psi_tw, iso_n, psi_so);
   };
 
   if (a.diagnose_only) {
@@ -112,44 +165,98 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     return;
   }
 
-  // carried streamfunctions -> stencils (the loop uses the previous diagnosis until it % K == 0)
-  {
-    double wA[LPL], t1[LPL], t2[LPL];
-    if (TW) pm::load_lev<LPL>(t1, (ISO ? M.Psi_iso_b : M.Psi_tw) + m * nz, nz, 0.0);
-    if (SO) pm::load_lev<LPL>(t2, M.Psi_so + m * nz, nz, 0.0);
+  const long long K = M.K, it_end = a.it0 + a.nsteps;
+  // carried streamfunctions -> stencils (the loop uses the previous diagnosis until it % K == 0);
+  // the 'jn' order diagnoses at the top of iteration it % K == 0 and then needs nothing carried
+  if (!ML || a.it0 % K != 0) {
+    double t1[LPL], t2[LPL], t3[LPL];
     PM_UNROLL
-    for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? t1[j] : 0.0) - (SO ? t2[j] : 0.0)) * 1e6;
-    pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
-    if (NORTH) {
-      pm::load_lev<LPL>(t1, M.Psi_iso_n + m * nz, nz, 0.0);
-      PM_UNROLL
-      for (int j = 0; j < LPL; ++j) wA[j] = -t1[j] * 1e6;
-      pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
-    }
-  }
-  // boundary values of "plain" columns are invariant under the step: set them once
-  // (surface: column.py:230-231, bottom: column.py:232)
-  if (!cb.conv) pm::set_level<LPL>(cb.b, nz - 1, cb.bs);
-  if (cb.plain) col_bottom<LPL>(cb, zs);
-  if (NORTH) {
-    if (!cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
-    if (cn.plain) col_bottom<LPL>(cn, zs);
+    for (int j = 0; j < LPL; ++j) t1[j] = t2[j] = t3[j] = 0.0;
+    if (TW) pm::load_lev<LPL>(t1, (ISO ? M.Psi_iso_b : M.Psi_tw) + m * nz, nz, 0.0);
+    if (NORTH) pm::load_lev<LPL>(t2, M.Psi_iso_n + m * nz, nz, 0.0);
+    if (SO) pm::load_lev<LPL>(t3, M.Psi_so + m * nz, nz, 0.0);
+    apply(t1, t2, t3);
   }
 
-  const long long K = M.K, it_end = a.it0 + a.nsteps;
-  // last iteration of this launch that re-diagnoses: only that one writes diagnostics to HBM
-  const long long last_refresh = ((it_end - 1) / K) * K;
-  long long ii = a.it0;
-  while (ii < it_end) {
-    const long long stop = ((ii + K - 1) / K) * K;  // next iteration with it % K == 0
-    const bool hits = stop < it_end;
-    const int n = (int)((hits ? stop + 1 : it_end) - ii);
-    for (int s = 0; s < n; ++s) {
-      col_advance<LPL>(cb, G, nz);
-      if (NORTH) col_advance<LPL>(cn, G, nz);
+  if (!ML) {
+    // boundary values of "plain" columns are invariant under the step: set them once
+    // (surface: column.py:230-231, bottom: column.py:232)
+    if (!cb.conv) pm::set_level<LPL>(cb.b, nz - 1, cb.bs);
+    if (cb.plain) col_bottom<LPL>(cb, zs);
+    if (NORTH) {
+      if (!cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
+      if (cn.plain) col_bottom<LPL>(cn, zs);
     }
-    ii += n;
-    if (hits) refresh(stop == last_refresh);
+    // last iteration of this launch that re-diagnoses: only that one writes diagnostics to HBM
+    const long long last_refresh = ((it_end - 1) / K) * K;
+    long long ii = a.it0;
+    while (ii < it_end) {
+      const long long stop = ((ii + K - 1) / K) * K;  // next iteration with it % K == 0
+      const bool hits = stop < it_end;
+      const int n = (int)((hits ? stop + 1 : it_end) - ii);
+      for (int s = 0; s < n; ++s) {
+        col_advance<LPL>(cb, G, nz);
+        if (NORTH) col_advance<LPL>(cn, G, nz);
+      }
+      ii += n;
+      if (hits) refresh(stop == last_refresh);
+    }
+  } else {
+    // examples/run_JansenNadeau_2018.py:201-261 / run_single_global_basin.py:172-229
+    const long long last_refresh = ((it_end - 1) / K) * K;
+    const bool two_var_b = M.basin.nvar > 1, two_var_n = M.north.nvar > 1;
+    long long ii = a.it0;
+    while (ii < it_end) {
+      if (ii % K == 0) refresh(ii == last_refresh);
+      long long stop = (ii / K + 1) * K;
+      if (stop > it_end) stop = it_end;
+      for (; ii < stop; ++ii) {
+        // bottom boundary condition and bottom-boundary-layer kappa (:233-254); levels 0 and 1
+        // of both columns and bs[0] live in lane 0
+        const double bb0 = rt::shfl(cb.b[0], 0), bb1 = rt::shfl(cb.b[1], 0);
+        const double nb0 = rt::shfl(cn.b[0], 0), nb1 = rt::shfl(cn.b[1], 0);
+        const double bs0 = rt::shfl(ml.bs[0], 0);
+        int vb = cb.var, vn = cn.var;
+        if (psi_so1 < 0) {
+          cb.bbot = bs0;
+          vb = 1;
+        }
+        if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) {
+          cb.bbot = nb0;
+          vb = 1;
+        } else if (psi_so1 >= 0) {
+          cb.bbot = bb1;
+          vb = 0;
+        }
+        if (res_n1 < 0 && bb0 < nb1) {
+          cn.bbot = bb0;
+          vn = 1;
+        } else {
+          cn.bbot = nb1;
+          vn = 0;
+        }
+        if (two_var_b) cb.var = vb;
+        if (two_var_n) cn.var = vn;
+        col_advance_exact<LPL>(cb, xb, EG, G, nz, dt);
+        col_advance_exact<LPL>(cn, xn, EG, G, nz, dt);
+        const bool sorted = pm::ml_bind_basin<LPL>(cb.b, nz, bb_s);
+        pm::ml_step(ml, bb_s, pm_s, nz, sorted, ws + sp.w_bs, dt, &status);
+      }
+    }
+    if (L == 0) {
+      M.basin.bbot[m] = cb.bbot;
+      M.north.bbot[m] = cn.bbot;
+      if (M.basin.var) M.basin.var[m] = cb.var;
+      if (M.north.var) M.north.var[m] = cn.var;
+    }
+    PM_UNROLL
+    for (int e = 0; e < pm::kMLP; ++e) {
+      const int k = pm::mlk(e);
+      if (k < ny) {
+        M.ml_bs[m * ny + k] = ml.bs[e];
+        if (M.ml_Psi_s) M.ml_Psi_s[m * ny + k] = ml.ps[e];
+      }
+    }
   }
 
   pm::store_lev<LPL>(cb.b, M.basin.b + m * nz, nz);
@@ -162,13 +269,18 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       if (NORTH) bad |= !(fabs(cn.b[j]) <= 1.79e308);
     }
   }
+  if (ML) {
+    PM_UNROLL
+    for (int e = 0; e < pm::kMLP; ++e)
+      if (pm::mlk(e) < ny) bad |= !(fabs(ml.bs[e]) <= 1.79e308);
+  }
   if (rt::ballot(bad)) status |= PMOC_ST_NAN;
   if (M.status && L == 0) M.status[m] |= status;
 }
 
 template <int LPL>
 int launch_model(const RunArgs& ra, void* stream) {
-  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO);
+  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML);
   const long long grid = blocks_for(ra.m.M);
   const int block = 32 * kWarpsPerBlock;
   const size_t smem = ra.sp.bytes(kWarpsPerBlock);
@@ -180,6 +292,9 @@ int launch_model(const RunArgs& ra, void* stream) {
       return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO>, grid, block, smem, stream, ra);
     case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO:
       return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO>, grid, block, smem, stream, ra);
+    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML:
+      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML>, grid, block, smem,
+                    stream, ra);
     default: return fail(PMOC_EUNSUPPORTED, "module combination has no fused kernel");
   }
 }

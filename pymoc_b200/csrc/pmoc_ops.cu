@@ -139,6 +139,68 @@ PM_GLOBAL void k_so(SoArgs a) {
   if (a.status && L == 0) a.status[m] |= status;
 }
 
+struct MlArgs {
+  pmoc_model m;
+  pmoc_vec b_basin, Psi_b;
+  double dt;
+  uint32_t* status;
+  int nzp, nyp;
+};
+
+// SO_ML.timestep for every member: one warp per member, b_basin / Psi_b staged in shared memory
+PM_GLOBAL void k_ml(MlArgs a) {
+  const pmoc_model& M = a.m;
+  const int nz = M.nz, ny = M.ny, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
+  double* ysm = rt::smem();
+  double* ws = ysm + a.nyp + (size_t)(2 * a.nzp + a.nyp + 320) * W;
+  double *bb_s = ws, *pm_s = ws + a.nzp, *bs_s = ws + 2 * a.nzp, *scan_s = bs_s + a.nyp;
+  for (int i = W * 32 + L; i < a.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
+  rt::syncblock();
+  const long long m = rt::block_idx() * rt::warps_per_block() + W;
+  if (m >= M.M) return;
+  const double* bb = vrow(a.b_basin, m);
+  const double* pb = vrow(a.Psi_b, m);
+  int fnz = 0x7fffffff, fpos = 0x7fffffff;
+  bool bad = false;
+  for (int i = L; i < nz; i += 32) {
+    const double v = pb[i];
+    bb_s[i] = bb[i];
+    pm_s[i] = v;
+    if (v != 0.0 && i < fnz) fnz = i;
+    if (v > 0.0 && i < fpos) fpos = i;
+    if (i < nz - 1) bad |= !(bb[i + 1] >= bb[i]);
+  }
+  fnz = rt::min_i(fnz);
+  fpos = rt::min_i(fpos);
+  const bool sorted = rt::ballot(bad) == 0;
+  rt::syncwarp();
+  unsigned status = 0;
+  if (fnz == 0x7fffffff) {
+    status |= PMOC_ST_ML_INDEX;
+  } else {
+    const double held = pm_s[fnz];
+    rt::syncwarp();
+    for (int i = L; i < fnz; i += 32) pm_s[i] = held;
+  }
+  rt::syncwarp();
+  pm::MlState S{};
+  pm::ml_setup(S, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m), vrow(M.ml_surflux, m),
+               vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), a.dt, scan_s);
+  S.first_pos = fpos == 0x7fffffff ? -1 : fpos;
+  PM_UNROLL
+  for (int e = 0; e < pm::kMLP; ++e) S.bs[e] = M.ml_bs[m * ny + (pm::mlk(e) < ny ? pm::mlk(e) : ny - 1)];
+  pm::ml_step(S, bb_s, pm_s, nz, sorted, bs_s, a.dt, &status);
+  PM_UNROLL
+  for (int e = 0; e < pm::kMLP; ++e) {
+    const int k = pm::mlk(e);
+    if (k < ny) {
+      M.ml_bs[m * ny + k] = S.bs[e];
+      if (M.ml_Psi_s) M.ml_Psi_s[m * ny + k] = S.ps[e];
+    }
+  }
+  if (a.status && L == 0) a.status[m] |= status;
+}
+
 static int lpl_for(int nz) { return nz <= 64 ? 2 : (nz + 31) / 32; }
 
 #define PM_DISPATCH_LPL(nz, CALL)                          \
@@ -183,7 +245,20 @@ int check_model(const pmoc_model* m) {
     if (m->so_tau_on_y) return fail(PMOC_EUNSUPPORTED, "tau on the y grid is not implemented yet");
     if (m->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "F2010 BVP smoother (c != None) is not implemented yet");
   }
-  if (f & (PMOC_HAS_ML | PMOC_ORDER_JN)) return fail(PMOC_EUNSUPPORTED, "SO_ML / 'jn' order not implemented yet");
+  if (((f & PMOC_HAS_ML) != 0) != ((f & PMOC_ORDER_JN) != 0))
+    return fail(PMOC_EUNSUPPORTED, "SO_ML is stepped by the 'jn' loop order only (and that order needs SO_ML)");
+  if (f & PMOC_HAS_ML) {
+    const unsigned need = PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO;
+    if ((f & need) != need) return fail(PMOC_EINVAL, "the 'jn' order needs basin + north + thermal wind (iso) + Psi_SO");
+    if (m->ny < 3 || m->ny > PMOC_MAX_NY_ML) return fail(PMOC_EUNSUPPORTED, "SO_ML needs 3 <= ny <= 64");
+    if (!m->ml_bs || !m->ml_Ks.ptr || !m->ml_h.ptr || !m->ml_L.ptr || !m->ml_vpist.ptr || !m->ml_surflux.ptr ||
+        !m->ml_rest_mask.ptr || !m->ml_b_rest.ptr)
+      return fail(PMOC_EINVAL, "SO_ML parameters incomplete");
+    if (!m->basin.do_conv || !m->north.do_conv) return fail(PMOC_EINVAL, "the 'jn' order steps both columns with do_conv");
+    if (m->basin.bzbot.ptr || m->north.bzbot.ptr) return fail(PMOC_EINVAL, "the 'jn' order sets bbot; bzbot must be NULL");
+    if ((m->basin.nvar > 1 && !m->basin.var) || (m->north.nvar > 1 && !m->north.var))
+      return fail(PMOC_EINVAL, "kappa variants need the var arrays");
+  }
   return PMOC_OK;
 }
 
@@ -299,8 +374,19 @@ int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, do
   return PMOC_OK;
 }
 
-int pmoc_ml_timestep(const pmoc_model*, pmoc_vec, pmoc_vec, double, uint32_t*, void*) {
-  return fail(PMOC_EUNSUPPORTED, "SO_ML is not implemented yet");
+int pmoc_ml_timestep(const pmoc_model* ml, pmoc_vec b_basin, pmoc_vec Psi_b, double dt, uint32_t* status, void* stream) {
+  if (!ml || ml->M <= 0 || ml->nz < 2 || !ml->y || !b_basin.ptr || !Psi_b.ptr) return fail(PMOC_EINVAL, "bad SO_ML arguments");
+  if (ml->ny < 3 || ml->ny > PMOC_MAX_NY_ML) return fail(PMOC_EUNSUPPORTED, "SO_ML needs 3 <= ny <= 64");
+  if (!ml->ml_bs || !ml->ml_Ks.ptr || !ml->ml_h.ptr || !ml->ml_L.ptr || !ml->ml_vpist.ptr || !ml->ml_surflux.ptr ||
+      !ml->ml_rest_mask.ptr || !ml->ml_b_rest.ptr)
+    return fail(PMOC_EINVAL, "SO_ML parameters incomplete");
+  MlArgs a{};
+  a.m = *ml; a.b_basin = b_basin; a.Psi_b = Psi_b; a.dt = dt; a.status = status;
+  a.nzp = (ml->nz + 3) & ~3;
+  a.nyp = (ml->ny + 3) & ~3;
+  const size_t smem = sizeof(double) * (size_t)(a.nyp + (2 * a.nzp + a.nyp + 320) * kWarpsPerBlock);
+  if (smem > 200 * 1024) return fail(PMOC_EUNSUPPORTED, "nz too large for the stand-alone SO_ML kernel");
+  return launch(k_ml, blocks_for(ml->M), 32 * kWarpsPerBlock, smem, stream, a);
 }
 
 }  // extern "C"

@@ -3,3 +3,4 @@
 from .column import Column
 from .psi_SO import Psi_SO
 from .psi_thermwind import Psi_Thermwind
+from .SO_ML import SO_ML

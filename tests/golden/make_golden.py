@@ -342,16 +342,28 @@ def check_callable_sampling():
 
 
 if __name__ == '__main__':
-  unit_fixture()
-  print('units done', flush=True)
-  if 'units' in sys.argv[1:]:
-    sys.exit(0)
-  GAP = check_callable_sampling()
-  coupled_fixture('c1.npz', configs.c1_timestepping(1), [0], [1, 2, 10, 300, 1200], extra=dict(callable_init_gap=GAP))
-  coupled_fixture('c2.npz', configs.c2_column_so(16, ntau=4), [0, 5, 10, 15], [1, 73, 720, 2160])
-  coupled_fixture('twocol.npz', configs.twocol(1), [0], [1, 25, 480])
-  coupled_fixture('c3.npz', configs.c3_twocol_so(16, axes=(2, 2, 2, 2)), [0, 7, 9, 15], [1, 25, 480, 2400])
-  coupled_fixture('c3_bvp.npz', configs.c3_twocol_so(1, c=0.1), [0], [1, 25, 240])
-  coupled_fixture('c4.npz', configs.c4_jansen_nadeau(32, axes=(2, 2, 2, 2, 2)), [0, 13, 22, 31], [1, 12, 13, 600, 2400])
-  coupled_fixture('c4_literal.npz', configs.c4_jansen_nadeau(1), [0], [1, 120, 1200])
-  coupled_fixture('c5.npz', configs.c5_single_global_basin(1), [0], [1, 24, 25, 480])
+  # `make_golden.py only c4 c5` regenerates just the named coupled fixtures
+  only = sys.argv[sys.argv.index('only') + 1:] if 'only' in sys.argv else None
+  want = lambda name: only is None or name in only
+  if only is None:
+    unit_fixture()
+    print('units done', flush=True)
+    if 'units' in sys.argv[1:]:
+      sys.exit(0)
+  if want('c1'):
+    GAP = check_callable_sampling()
+    coupled_fixture('c1.npz', configs.c1_timestepping(1), [0], [1, 2, 10, 300, 1200], extra=dict(callable_init_gap=GAP))
+  if want('c2'):
+    coupled_fixture('c2.npz', configs.c2_column_so(16, ntau=4), [0, 5, 10, 15], [1, 73, 720, 2160])
+  if want('twocol'):
+    coupled_fixture('twocol.npz', configs.twocol(1), [0], [1, 25, 480])
+  if want('c3'):
+    coupled_fixture('c3.npz', configs.c3_twocol_so(16, axes=(2, 2, 2, 2)), [0, 7, 9, 15], [1, 25, 480, 2400])
+  if want('c3_bvp'):
+    coupled_fixture('c3_bvp.npz', configs.c3_twocol_so(1, c=0.1), [0], [1, 25, 240])
+  if want('c4'):
+    coupled_fixture('c4.npz', configs.c4_jansen_nadeau(32, axes=(2, 2, 2, 2, 2)), [0, 13, 22, 31], [1, 12, 13, 600, 2400])
+  if want('c4_literal'):
+    coupled_fixture('c4_literal.npz', configs.c4_jansen_nadeau(1), [0], [1, 120, 1200])
+  if want('c5'):
+    coupled_fixture('c5.npz', configs.c5_single_global_basin(1), [0], [1, 24, 25, 480])

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import golden, relmax
-from pymoc_b200.modules import Column, Psi_SO, Psi_Thermwind
+from pymoc_b200.modules import SO_ML, Column, Psi_SO, Psi_Thermwind
 
 TOL = 1e-10
 
@@ -176,3 +176,54 @@ def so_checks():
     assert np.array_equal(so.Psi_Ek, out['Psi_Ek']), i  # same operations in the same order: bit exact
     ys = np.array([so.ys(v) for v in inp['b'][::8]])
     assert np.abs(ys - out['ys'][::8]).max() < 1e-6, i  # metres; brentq's own tolerance is ~4e-9 m
+
+
+# -------------------------------------------------------------------------------- SO_ML
+def ml_checks():
+  with pytest.raises(TypeError) as e:
+    SO_ML(y=100)
+  assert str(e.value) == 'y needs to be numpy array providing (regular) grid'
+  # tests/modules/test_SO_ML.py:92-127
+  dt = 60 * 86400
+  conf = {'y': np.asarray(np.linspace(0, 2.0e6, 51)), 'Ks': 100, 'h': 50, 'L': 4e6, 'surflux': 5.9e3, 'rest_mask': 0.0,
+          'b_rest': 0.0, 'v_pist': 2.0 / 86400.0, 'bs': 0.02}
+  b_basin = np.linspace(0.03, -0.002, 80)
+  Psi_b = np.linspace(4.0e6, 0, 80)
+  a, b = SO_ML(**conf), SO_ML(**conf)
+  with pytest.raises(TypeError) as e:
+    a.timestep(dt=dt, Psi_b=Psi_b)
+  assert str(e.value) == 'b_basin needs to be numpy array providing buoyancy levels in basin'
+  with pytest.raises(TypeError) as e:
+    a.timestep(dt=dt, b_basin=b_basin)
+  assert str(e.value) == 'Psi_b needs to be numpy array providing overturning at buoyancy levels given by b_basin'
+  a.timestep(dt=dt, b_basin=b_basin, Psi_b=Psi_b)
+  b.advdiff(b_basin=b_basin, Psi_b=Psi_b, dt=dt)
+  assert all(a.bs == b.bs) and all(a.Psi_s == b.Psi_s)
+  # the same call against the oracle (decreasing b_basin: numpy's guess-carrying search decides)
+  from oracle import pymoc_oracle as O
+  ref = O.MixedLayerState(**{k: (float(v) if not isinstance(v, np.ndarray) else v) for k, v in conf.items()})
+  O.ml_timestep(ref, b_basin, Psi_b, dt)
+  assert relmax(a.bs, ref.bs) < TOL and relmax(a.Psi_s, ref.Psi_s) < TOL, (relmax(a.bs, ref.bs), relmax(a.Psi_s, ref.Psi_s))
+  # test_SO_ML.py:129-170 (5 % against the analytic tendency)
+  y = np.asarray(np.linspace(0, 2.0e6, 51))
+  Ks, L, h, surflux = 100, 4e6, 50, 5.9e3
+  dtheta_dy = 2.0 * np.pi / 2.0e6
+  b_basin = np.asarray([0.02 * (n / 2.0e6)**2 for n in y])
+  bs = np.asarray([b_basin[-1] * np.cos(n * dtheta_dy) for n in y])
+  Psi_b = np.asarray(np.linspace(1e4, 2.0e4, 51))
+  ml = SO_ML(y=y, Ks=Ks, h=h, L=L, surflux=surflux, rest_mask=0.0, b_rest=0.0, v_pist=2.0 / 86400.0, bs=bs)
+  dbs_dy = np.asarray([-dtheta_dy * b_basin[-1] * np.sin(n * dtheta_dy) for n in y])
+  d2bs_dy2 = np.asarray([-dtheta_dy**2 * b_basin[-1] * np.cos(n * dtheta_dy) for n in y])
+  db = -((Psi_b / (h * L)) * dbs_dy + Ks * d2bs_dy2 + surflux / h) * dt
+  want = -(ml.bs.copy() + db)
+  ml.advdiff(b_basin, Psi_b, dt)
+  assert all(np.abs(want[i] - ml.bs[i]) / want[i] < 0.05 for i in range(len(want)))
+  # fixtures produced by the reference's SO_ML.timestep
+  for i, d in golden('units')['ml'].items():
+    inp, out = d['inp'], d['out']
+    ml = SO_ML(y=inp['y'], Ks=inp['Ks'], h=inp['h'], L=inp['L'], surflux=inp['surflux'].copy(),
+               rest_mask=inp['rest_mask'].copy(), b_rest=inp['b_rest'].copy(), v_pist=inp['v_pist'], bs=inp['bs'].copy())
+    for step in range(out['bs'].shape[0]):  # five successive steps
+      ml.timestep(b_basin=inp['b_basin'], Psi_b=inp['Psi_b'], dt=inp['dt'])
+      assert relmax(ml.Psi_s, out['Psi_s'][step]) < TOL, (i, step, relmax(ml.Psi_s, out['Psi_s'][step]))
+      assert relmax(ml.bs, out['bs'][step]) < TOL, (i, step, relmax(ml.bs, out['bs'][step]))

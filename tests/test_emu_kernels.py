@@ -17,11 +17,12 @@ def emu():
   return EmuBackend()
 
 
-@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 720), ('twocol', 480), ('c3', 480)])
+@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 720), ('twocol', 480), ('c3', 480), ('c4', 600), ('c4_literal', 120),
+                                       ('c5', 480)])
 def test_fused_kernel_vs_reference(emu, name, nmax):
   run_against_golden(emu, name, nmax)
 
 
-@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25)])
+@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25), ('c4', 13)])
 def test_short_launches_carry_streamfunctions(emu, name, nmax):
   run_against_golden(emu, name, nmax, chunked=True)

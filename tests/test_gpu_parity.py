@@ -23,13 +23,14 @@ def cuda():
   return CudaBackend()
 
 
-@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 2160), ('twocol', 480), ('c3', 2400)])
+@pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 2160), ('twocol', 480), ('c3', 2400), ('c4', 2400),
+                                       ('c4_literal', 1200), ('c5', 480)])
 def test_fused_kernel_vs_reference(cuda, name, nmax):
   worst = run_against_golden(cuda, name, nmax)
   print('%s: worst relative error %.2e' % (name, worst))
 
 
-@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25)])
+@pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25), ('c4', 600)])
 def test_short_launches_carry_streamfunctions(cuda, name, nmax):
   run_against_golden(cuda, name, nmax, chunked=True)
 

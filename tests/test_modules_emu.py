@@ -31,3 +31,7 @@ def test_thermwind():
 
 def test_so():
   mc.so_checks()
+
+
+def test_ml():
+  mc.ml_checks()
