@@ -48,6 +48,7 @@ typedef struct {
 #define PMOC_ST_BRENT_SIGN 4u     /* f(a), f(b) same sign: scipy.optimize.brentq would raise ValueError */
 #define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML:
                                      numpy's guess-carrying search is followed query by query */
+#define PMOC_ST_BVP_SERIES 32u    /* F2010 smoother: a cell propagator series did not converge (N2 h^2/c^2 huge) */
 #define PMOC_ST_ML_INDEX 16u      /* SO_ML needed np.argwhere(Psi_b > 0)[0][0] / np.nonzero(Psi_b)[0][0] of an
                                      all-non-positive / all-zero Psi_b: the reference raises IndexError */
 
@@ -72,6 +73,8 @@ typedef struct {
 #define PMOC_ISO 4u       /* force columns with Psibz() instead of Psi (psi_thermwind.py:187-208) */
 #define PMOC_HAS_SO 8u    /* Psi_SO on the basin column                                   */
 #define PMOC_HAS_ML 16u   /* SO_ML mixed layer                                            */
+#define PMOC_SO_BVP 64u   /* set by the library when so_c.ptr != NULL: F2010 smoother of Psi_GM
+                             (psi_SO.py:308-323); callers leave it clear */
 #define PMOC_ORDER_JN 32u /* loop order + bottom-boundary switches of
                              examples/run_JansenNadeau_2018.py:201-261; otherwise the order of
                              examples/example_twocol_plusSO.py:99-115 */

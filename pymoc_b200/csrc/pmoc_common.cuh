@@ -44,7 +44,7 @@ struct SmemPlan {
   int off_dzu, off_rdzu, off_dzc, off_rdzc;                        // per block, bit-faithful step only
   int off_warp0, per_warp;                                          // per warp region
   int w_col[2];                                                     // column tables of basin / north (4*nzp each)
-  int w_ctop, w_crinv, w_cu, w_psib, w_bs, w_sinv;
+  int w_ctop, w_crinv, w_cu, w_psib, w_bs, w_sinv, w_tau, w_bvp;
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
@@ -86,6 +86,8 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   if (flags & PMOC_HAS_SO) {
     s.w_bs = w; w += s.nyp;
     s.w_sinv = w; w += s.nyp;
+    s.w_tau = w; w += s.nyp;
+    if (flags & PMOC_SO_BVP) { s.w_bvp = w; w += 4 * s.nzp; }
   }
   if (exact) {
     const int r0 = w;

@@ -592,6 +592,10 @@ PM_DEV double mean100(double tau) {
 struct SoPar {
   double tau_ave, f, rho, L, KGM, smax;
   const double *sill, *ektap, *toptap, *bottap;  // [nz] natural order, global
+  const double* tau_y;                           // tau on the y grid (shared memory) or nullptr for a float tau
+  double c;                                      // F2010 phase speed (BVP branch only)
+  int with_Ek;
+  double* bvp_s;                                 // 4*nzp doubles of scratch (BVP branch only)
 };
 struct SoSurf {  // per-refresh scan of bs(y)
   double mn, bsN, y0, yN;
@@ -623,18 +627,176 @@ PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int n
   return s;
 }
 
-// Psi_SO.solve with the explicit GM branch (psi_SO.py:106-140, 218-243, 302-354).  Sv.
+// np.mean(tau(np.linspace(y0, yN, 100))) for tau given on the y grid (psi_SO.py:239):
+// numpy's linspace (arange*step + start, last point = stop), np.interp and the pairwise
+// reduction of 100 terms (8 accumulators over 96 terms, tree combine, 4 trailing adds).
+PM_DEV double tau_mean100(double y0, double yN, const double* ygrid, const double* tau_y, int ny) {
+  const double delta = yN - y0, step = delta / 99.0;
+  auto at = [&](int p) {
+    double yp;
+    if (p == 99)
+      yp = yN;
+    else if (step == 0.0)
+      yp = (double)p / 99.0 * delta + y0;
+    else
+      yp = (double)p * step + y0;
+    return interp1(yp, ygrid, tau_y, ny);
+  };
+  double r[8];
+  PM_UNROLL
+  for (int k = 0; k < 8; ++k) r[k] = at(k);
+  for (int blk = 1; blk < 12; ++blk) {
+    PM_UNROLL
+    for (int k = 0; k < 8; ++k) r[k] = r[k] + at(blk * 8 + k);
+  }
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (int p = 96; p < 100; ++p) res = res + at(p);
+  return res / 100.0;
+}
+
+// Propagators of u'' = (q0 + q1 s) u across cells of width h, by power series in s:
+//   u(h) = A u(0) + B u'(0),  u'(h) = C u(0) + D u'(0),  A D - B C = 1.
+// With t_k = a_k h^k the recurrence is t_{k+2} = (Q0 t_k + Q1 t_{k-1}) / ((k+2)(k+1)),
+// Q0 = q0 h^2, Q1 = q1 h^3; Bh = B/h.  All terms are positive for a stable stratification.
 template <int LPL>
+PM_DEV bool cell_propagators(const double (&Q0)[LPL], const double (&Q1)[LPL], double (&A)[LPL], double (&Bh)[LPL],
+                             double (&D)[LPL]) {
+  double am[LPL], ak[LPL], an[LPL], bm[LPL], bk[LPL], bn[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    am[j] = 0.; ak[j] = 1.; an[j] = 0.;
+    bm[j] = 0.; bk[j] = 0.; bn[j] = 1.;
+    A[j] = 1.; Bh[j] = 1.; D[j] = 1.;
+  }
+  for (int k = 0; k < 600; ++k) {
+    const double inv = 1.0 / ((double)(k + 2) * (double)(k + 1)), kk = (double)(k + 2);
+    bool big = false;
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const double na = (Q0[j] * ak[j] + Q1[j] * am[j]) * inv;
+      const double nb = (Q0[j] * bk[j] + Q1[j] * bm[j]) * inv;
+      big |= !((fabs(na) + fabs(an[j])) <= 1e-19 * fabs(A[j]));
+      big |= !((fabs(nb) + fabs(bn[j])) * kk <= 1e-19 * (fabs(Bh[j]) + fabs(D[j])));
+      A[j] = A[j] + na;
+      Bh[j] = Bh[j] + nb;
+      D[j] = D[j] + kk * nb;
+      am[j] = ak[j]; ak[j] = an[j]; an[j] = na;
+      bm[j] = bk[j]; bk[j] = bn[j]; bn[j] = nb;
+    }
+    if (k >= 3 && rt::ballot(big) == 0) return true;
+  }
+  return false;
+}
+
+// F2010 smoother of Psi_GM (psi_SO.py:308-323): y'' = N2(z)/c^2 (y - T(z)), Dirichlet ends.
+// N2 and T are piecewise linear on z (np.interp closures), so with u = y - T each cell obeys
+// u'' = q(s) u exactly; matching y' at the nodes gives a symmetric tridiagonal system for the
+// nodal values.  This is the converged solution of the ODE the reference hands to its
+// adaptive, tol=1e-3 solve_bvp (stated tolerance 1e-5).
+// In/out: g holds T on entry and the solution y on return (m^3/s).
+template <int LPL>
+PM_DEV void so_bvp(double (&g)[LPL], const double (&b)[LPL], double c, double ya, double yb, const double* zs, int nz,
+                   double* scratch, unsigned* status) {
+  const int nzp = 32 * LPL;
+  double *lo_s = scratch, *di_s = scratch + nzp, *up_s = scratch + 2 * nzp, *rh_s = scratch + 3 * nzp;
+  const double c2 = c * c;
+  // N2 (psi_SO.py:154-160) at the own levels and at the level above
+  const double bnext = rt::shfl_down(b[0], 1), bprev = rt::shfl_up(b[LPL - 1], 1);
+  double n2[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    const double up = j < LPL - 1 ? b[j + 1 < LPL ? j + 1 : j] : bnext;
+    const double dn = j > 0 ? b[j > 0 ? j - 1 : 0] : bprev;
+    double v = 0.0;
+    if (i < nz) {
+      if (i == 0)
+        v = (up - b[j]) / (zs[1] - zs[0]);
+      else if (i == nz - 1)
+        v = (b[j] - dn) / (zs[i] - zs[i - 1]);
+      else
+        v = (up - dn) / ((zs[i + 1] - zs[i]) + (zs[i] - zs[i - 1]));
+    }
+    n2[j] = v;
+  }
+  const double n2next = rt::shfl_down(n2[0], 1), gnext = rt::shfl_down(g[0], 1);
+  double Q0[LPL], Q1[LPL], h[LPL], Tp[LPL], A[LPL], Bh[LPL], D[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    const bool cell = i < nz - 1;
+    h[j] = cell ? zs[i + 1] - zs[i] : 1.0;
+    const double n2u = j < LPL - 1 ? n2[j + 1 < LPL ? j + 1 : j] : n2next;
+    const double gu = j < LPL - 1 ? g[j + 1 < LPL ? j + 1 : j] : gnext;
+    Q0[j] = cell ? n2[j] / c2 * h[j] * h[j] : 0.0;
+    Q1[j] = cell ? (n2u - n2[j]) / c2 * h[j] * h[j] : 0.0;  // slope * h^3
+    Tp[j] = cell ? (gu - g[j]) / h[j] : 0.0;
+  }
+  if (!cell_propagators<LPL>(Q0, Q1, A, Bh, D)) *status |= 32u;
+  double ib[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) ib[j] = 1.0 / (h[j] * Bh[j]);
+  const double ib_p = rt::shfl_up(ib[LPL - 1], 1), D_p = rt::shfl_up(D[LPL - 1], 1), Tp_p = rt::shfl_up(Tp[LPL - 1], 1);
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz) {
+      double lo = 0., di = 1., up = 0., rh;
+      if (i == 0)
+        rh = ya - g[j];
+      else if (i == nz - 1)
+        rh = yb - g[j];
+      else {
+        const double ibm = j > 0 ? ib[j > 0 ? j - 1 : 0] : ib_p, Dm = j > 0 ? D[j > 0 ? j - 1 : 0] : D_p;
+        const double Tpm = j > 0 ? Tp[j > 0 ? j - 1 : 0] : Tp_p;
+        lo = -ibm;
+        up = -ib[j];
+        di = Dm * ibm + A[j] * ib[j];
+        rh = Tp[j] - Tpm;
+      }
+      lo_s[i] = lo; di_s[i] = di; up_s[i] = up; rh_s[i] = rh;
+    }
+  }
+  rt::syncwarp();
+  // Thomas sweep (every lane runs it, lane 0 stores)
+  {
+    const bool w = rt::lane() == 0;
+    double cp = 0., dp = 0.;
+    for (int i = 0; i < nz; ++i) {
+      const double l = lo_s[i], r = 1.0 / (di_s[i] - l * cp);
+      cp = up_s[i] * r;
+      dp = (rh_s[i] - l * dp) * r;
+      if (w) { up_s[i] = cp; rh_s[i] = dp; }
+    }
+    double x = 0.;
+    for (int i = nz - 1; i >= 0; --i) {
+      x = rh_s[i] - up_s[i] * x;
+      if (w) di_s[i] = x;
+    }
+  }
+  rt::syncwarp();
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz) g[j] = g[j] + di_s[i];
+  }
+  rt::syncwarp();
+}
+
+// Psi_SO.solve (psi_SO.py:106-140, 218-243, 302-354): outcrop latitudes, Ekman transport, GM
+// transport with the explicit slope clip or (BVP) the F2010 smoother.  Sv.
+template <int LPL, bool BVP = false>
 PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], double (&ysv)[LPL],
                      const double (&b)[LPL], const double* ygrid, const double* bs, const double* sinv, int ny,
                      const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status) {
   if (!S.mono) *status |= 2u;
-  const double pre = P.tau_ave / P.f / P.rho * P.L;
+  const double pre0 = P.tau_ave / P.f / P.rho * P.L;
   const double c6 = 1e6, r6 = 1.0 / 1e6;
+  double dyv[LPL];
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
-    double e = 0., g = 0., ps = 0., yo = 0.;
+    double e = 0., g = 0., yo = 0., dy = 1.;
     if (i < nz) {
       const double bi = b[j];
       if (bi < S.mn)
@@ -648,23 +810,45 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
         yo = outcrop_brent(bi, ygrid, bs, ny, S.south, &bad);
         if (bad) *status |= 4u;
       }
+      const double pre = P.tau_y ? tau_mean100(yo, S.yN, ygrid, P.tau_y, ny) / P.f / P.rho * P.L : pre0;
       e = div_const(pre * P.sill[i] * P.ektap[i], c6, r6);
-      double dy = S.yN - yo;
+      dy = S.yN - yo;
       dy = 0.1 > dy ? 0.1 : dy;
-      const double s = zs[i] / dy, ms = -P.smax;
-      const double mx = (s >= ms || s != s) ? s : ms;
-      double t = P.KGM * mx * P.L * P.toptap[i] * P.bottap[i];
-      if (dy > S.yN - S.y0) {
-        const double alt = -e * 1e6;
-        t = (t >= alt || t != t) ? t : alt;
+      if (BVP) {
+        g = P.KGM * zs[i] / dy * P.L * P.toptap[i] * P.bottap[i];
+      } else {
+        const double s = zs[i] / dy, ms = -P.smax;
+        const double mx = (s >= ms || s != s) ? s : ms;
+        g = P.KGM * mx * P.L * P.toptap[i] * P.bottap[i];
       }
-      g = div_const(t, c6, r6);
-      ps = i == 0 ? 0. : e + g;
     }
     ek[j] = e;
     gm[j] = g;
-    psi[j] = ps;
+    dyv[j] = dy;
     ysv[j] = yo;
+  }
+  if (BVP) {
+    double ya = 0., yb = 0.;
+    if (P.with_Ek) {  // bc_GM, psi_SO.py:270-275
+      ya = -(get_level<LPL>(ek, 0) * 1e6);
+      yb = -(get_level<LPL>(ek, nz - 1) * 1e6);
+    }
+    so_bvp<LPL>(gm, b, P.c, ya, yb, zs, nz, P.bvp_s, status);
+  }
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    double t = gm[j], ps = 0., g = 0.;
+    if (i < nz) {
+      if (dyv[j] > S.yN - S.y0) {
+        const double alt = -ek[j] * 1e6;
+        t = (t >= alt || t != t) ? t : alt;
+      }
+      g = div_const(t, c6, r6);
+      ps = i == 0 ? 0. : ek[j] + g;
+    }
+    gm[j] = g;
+    psi[j] = ps;
   }
 }
 

@@ -12,6 +12,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
+  constexpr bool BVP = (TOPO & PMOC_SO_BVP) != 0;  // F2010 smoother of Psi_GM
   const pmoc_model& M = a.m;
   const SmemPlan& sp = a.sp;
   const int nz = M.nz, ny = M.ny, nb = M.nb;
@@ -60,7 +61,16 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   pm::SoPar so{};
   pm::SoSurf surf{};
   if (SO) {
-    so.tau_ave = pm::mean100(vat(M.so_tau, m));
+    so.tau_ave = M.so_tau_on_y ? 0.0 : pm::mean100(vat(M.so_tau, m));
+    so.tau_y = nullptr;
+    if (M.so_tau_on_y) {
+      const double* t = vrow(M.so_tau, m);
+      for (int i = L; i < sp.nyp; i += 32) ws[sp.w_tau + i] = t[i < ny ? i : ny - 1];
+      so.tau_y = ws + sp.w_tau;
+    }
+    so.c = BVP ? vat(M.so_c, m) : 0.0;
+    so.with_Ek = M.so_bvp_with_Ek;
+    so.bvp_s = BVP ? ws + sp.w_bvp : nullptr;
     so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
     so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
     so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
@@ -146,7 +156,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         rt::syncwarp();
         surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);
       }
-      pm::so_solve<LPL>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so, zs, nz, &status);
+      pm::so_solve<LPL, BVP>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so, zs, nz,
+                             &status);
       if (write) {
         pm::store_lev<LPL>(psi_so, M.Psi_so + m * nz, nz);
         if (M.Psi_Ek) pm::store_lev<LPL>(ek, M.Psi_Ek + m * nz, nz);
@@ -280,23 +291,26 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
 
 template <int LPL>
 int launch_model(const RunArgs& ra, void* stream) {
-  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML);
+  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP);
   const long long grid = blocks_for(ra.m.M);
   const int block = 32 * kWarpsPerBlock;
   const size_t smem = ra.sp.bytes(kWarpsPerBlock);
+#define PM_CASE(T) \
+  case (T): return launch(k_model<LPL, (T)>, grid, block, smem, stream, ra);
   switch (t) {
-    case PMOC_HAS_TW: return launch(k_model<LPL, PMOC_HAS_TW>, grid, block, smem, stream, ra);
-    case PMOC_HAS_SO: return launch(k_model<LPL, PMOC_HAS_SO>, grid, block, smem, stream, ra);
-    case PMOC_HAS_TW | PMOC_HAS_SO: return launch(k_model<LPL, PMOC_HAS_TW | PMOC_HAS_SO>, grid, block, smem, stream, ra);
-    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO:
-      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO>, grid, block, smem, stream, ra);
-    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO:
-      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO>, grid, block, smem, stream, ra);
-    case PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML:
-      return launch(k_model<LPL, PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML>, grid, block, smem,
-                    stream, ra);
+    PM_CASE(PMOC_HAS_TW)
+    PM_CASE(PMOC_HAS_SO)
+    PM_CASE(PMOC_HAS_SO | PMOC_SO_BVP)
+    PM_CASE(PMOC_HAS_TW | PMOC_HAS_SO)
+    PM_CASE(PMOC_HAS_TW | PMOC_HAS_SO | PMOC_SO_BVP)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_SO_BVP)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP)
     default: return fail(PMOC_EUNSUPPORTED, "module combination has no fused kernel");
   }
+#undef PM_CASE
 }
 
 }  // namespace pmk

@@ -106,14 +106,15 @@ struct SoArgs {
   int nzp, nyp;
 };
 
-template <int LPL>
+template <int LPL, bool BVP>
 PM_GLOBAL void k_so(SoArgs a) {
   const pmoc_model& M = a.m;
   const int nz = M.nz, ny = M.ny, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
   double* zs = rt::smem();
   double* ysm = zs + a.nzp + 4;
-  double* bss = ysm + a.nyp + (size_t)2 * a.nyp * W;
+  double* bss = ysm + a.nyp + (size_t)(3 * a.nyp + (BVP ? 4 * a.nzp : 0)) * W;
   double* sinv = bss + a.nyp;
+  double* tau_s = sinv + a.nyp;
   for (int i = W * 32 + L; i < a.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
   for (int i = W * 32 + L; i < a.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
   rt::syncblock();
@@ -123,15 +124,24 @@ PM_GLOBAL void k_so(SoArgs a) {
   for (int i = L; i < a.nyp; i += 32) bss[i] = src[i < ny ? i : ny - 1];
   rt::syncwarp();
   pm::SoPar so{};
-  so.tau_ave = pm::mean100(vat(M.so_tau, m));
+  so.tau_ave = M.so_tau_on_y ? 0.0 : pm::mean100(vat(M.so_tau, m));
+  if (M.so_tau_on_y) {
+    const double* t = vrow(M.so_tau, m);
+    for (int i = L; i < a.nyp; i += 32) tau_s[i] = t[i < ny ? i : ny - 1];
+    so.tau_y = tau_s;
+    rt::syncwarp();
+  }
   so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
   so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
   so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
+  so.c = BVP ? vat(M.so_c, m) : 0.0;
+  so.with_Ek = M.so_bvp_with_Ek;
+  so.bvp_s = tau_s + a.nyp;
   double b[LPL], psi[LPL], ek[LPL], gm[LPL], ysv[LPL];
   pm::load_lev<LPL>(b, vrow(a.b, m), nz, 0.0);
   unsigned status = 0;
   const pm::SoSurf surf = pm::so_scan(ysm, bss, sinv, ny);
-  pm::so_solve<LPL>(psi, ek, gm, ysv, b, ysm, bss, sinv, ny, surf, so, zs, nz, &status);
+  pm::so_solve<LPL, BVP>(psi, ek, gm, ysv, b, ysm, bss, sinv, ny, surf, so, zs, nz, &status);
   pm::store_lev<LPL>(psi, a.Psi + m * nz, nz);
   if (a.Psi_Ek) pm::store_lev<LPL>(ek, a.Psi_Ek + m * nz, nz);
   if (a.Psi_GM) pm::store_lev<LPL>(gm, a.Psi_GM + m * nz, nz);
@@ -242,8 +252,6 @@ int check_model(const pmoc_model* m) {
         !m->so_smax.ptr || !m->so_sill_taper || !m->so_ek_taper || !m->so_top_taper || !m->so_bot_taper || !m->Psi_so)
       return fail(PMOC_EINVAL, "Psi_SO parameters incomplete");
     if (!(f & PMOC_HAS_ML) && !m->so_bs.ptr) return fail(PMOC_EINVAL, "so_bs missing");
-    if (m->so_tau_on_y) return fail(PMOC_EUNSUPPORTED, "tau on the y grid is not implemented yet");
-    if (m->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "F2010 BVP smoother (c != None) is not implemented yet");
   }
   if (((f & PMOC_HAS_ML) != 0) != ((f & PMOC_ORDER_JN) != 0))
     return fail(PMOC_EUNSUPPORTED, "SO_ML is stepped by the 'jn' loop order only (and that order needs SO_ML)");
@@ -268,11 +276,13 @@ int run_model(const pmoc_model* m, long long it0, long long nsteps, int diagnose
   if (!diagnose_only && nsteps == 0) return PMOC_OK;
   RunArgs ra;
   ra.m = *m;
+  ra.m.flags &= ~PMOC_SO_BVP;
+  if ((m->flags & PMOC_HAS_SO) && m->so_c.ptr) ra.m.flags |= PMOC_SO_BVP;
   ra.it0 = it0;
   ra.nsteps = nsteps;
   ra.diagnose_only = diagnose_only;
   const int lpl = lpl_for(m->nz);
-  ra.sp = plan_smem(lpl, m->ny, m->nb, m->flags);
+  ra.sp = plan_smem(lpl, m->ny, m->nb, ra.m.flags);
   switch (lpl) {
     case 2: return pmoc_launch_model_2(ra, stream);
     case 3: return pmoc_launch_model_3(ra, stream);
@@ -361,15 +371,15 @@ int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, do
   if (!so->so_tau.ptr || !so->so_f.ptr || !so->so_rho.ptr || !so->so_L.ptr || !so->so_KGM.ptr || !so->so_smax.ptr ||
       !so->so_sill_taper || !so->so_ek_taper || !so->so_top_taper || !so->so_bot_taper)
     return fail(PMOC_EINVAL, "Psi_SO parameters incomplete");
-  if (so->so_tau_on_y) return fail(PMOC_EUNSUPPORTED, "tau on the y grid is not implemented yet");
-  if (so->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "F2010 BVP smoother (c != None) is not implemented yet");
   SoArgs a{};
   a.m = *so; a.b = b; a.bs = bs; a.Psi = Psi; a.Psi_Ek = Psi_Ek; a.Psi_GM = Psi_GM; a.ys = ys; a.status = status;
   a.nyp = (so->ny + 3) & ~3;
+  const bool bvp = so->so_c.ptr != nullptr;
   PM_DISPATCH_LPL(so->nz, {
     a.nzp = 32 * LPL;
-    return launch(k_so<LPL>, blocks_for(so->M), 32 * kWarpsPerBlock,
-                  sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + 2 * a.nyp * kWarpsPerBlock), stream, a);
+    const size_t smem = sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + (3 * a.nyp + (bvp ? 4 * a.nzp : 0)) * kWarpsPerBlock);
+    if (bvp) return launch(k_so<LPL, true>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
+    return launch(k_so<LPL, false>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
   });
   return PMOC_OK;
 }

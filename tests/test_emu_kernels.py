@@ -26,3 +26,10 @@ def test_fused_kernel_vs_reference(emu, name, nmax):
 @pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25), ('c4', 13)])
 def test_short_launches_carry_streamfunctions(emu, name, nmax):
   run_against_golden(emu, name, nmax, chunked=True)
+
+
+def test_f2010_smoother_literal_c3(emu):
+  """examples/example_twocol_plusSO.py as written (c=0.1, bvp_with_Ek=True): the reference's adaptive
+  solve_bvp (tol=1e-3) against the converged solution of the same ODE; stated tolerance 1e-5."""
+  worst = run_against_golden(emu, 'c3_bvp', 240, tol=1e-5)
+  assert worst > 1e-12  # the two are different discretisations; a tiny number would mean the test is vacuous

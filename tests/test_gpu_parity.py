@@ -30,6 +30,13 @@ def test_fused_kernel_vs_reference(cuda, name, nmax):
   print('%s: worst relative error %.2e' % (name, worst))
 
 
+def test_f2010_smoother_literal_c3(cuda):
+  """examples/example_twocol_plusSO.py as written (c=0.1, bvp_with_Ek=True): the reference's adaptive
+  solve_bvp (tol=1e-3) against the converged solution of the same ODE; stated tolerance 1e-5."""
+  worst = run_against_golden(cuda, 'c3_bvp', 240, tol=1e-5)
+  print('c3_bvp: worst relative error %.2e' % worst)
+
+
 @pytest.mark.parametrize('name,nmax', [('c2', 73), ('c3', 25), ('c4', 600)])
 def test_short_launches_carry_streamfunctions(cuda, name, nmax):
   run_against_golden(cuda, name, nmax, chunked=True)
