@@ -49,6 +49,10 @@ typedef struct {
 #define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML:
                                      numpy's guess-carrying search is followed query by query */
 #define PMOC_ST_BVP_SERIES 32u    /* F2010 smoother: a cell propagator series did not converge (N2 h^2/c^2 huge) */
+#define PMOC_ST_NOISE_SWITCH 64u  /* 'jn' order: a bottom-boundary switch compared a streamfunction value that is
+                                     rounding noise (0 < |Psi[1]| < 1e-12 max|Psi|) with zero
+                                     (run_JansenNadeau_2018.py:233-254): the reference's own branch is then
+                                     decided by summation order, parity for this member is undefined */
 #define PMOC_ST_ML_INDEX 16u      /* SO_ML needed np.argwhere(Psi_b > 0)[0][0] / np.nonzero(Psi_b)[0][0] of an
                                      all-non-positive / all-zero Psi_b: the reference raises IndexError */
 

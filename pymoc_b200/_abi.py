@@ -8,7 +8,7 @@ STATUS_NAMES = {1: 'EINVAL', 2: 'EUNSUPPORTED', 3: 'ECUDA', 4: 'ENODEVICE'}
 
 HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP = 1, 2, 4, 8, 16, 32, 64
 STAGE_CONVECT, STAGE_VERTADVDIFF, STAGE_HORADV = 1, 2, 4
-ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES = 1, 2, 4, 8, 16, 32
+ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES, ST_NOISE_SWITCH = 1, 2, 4, 8, 16, 32, 64
 
 c_double_p = C.POINTER(C.c_double)
 

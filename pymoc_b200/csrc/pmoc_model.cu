@@ -114,6 +114,17 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       res_b1 = pm::get_level<LPL>(north_leg, 1);
       res_n1 = pm::get_level<LPL>(iso_n, 1);
       if (!pm::ml_bind_psi<LPL>(ml, psi_so, nz, pm_s)) status |= PMOC_ST_ML_INDEX;
+      double mx = 0.0;
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) {
+        const double a1 = fabs(north_leg[j]), a2 = fabs(iso_n[j]), a3 = fabs(psi_so[j]);
+        mx = a1 > mx ? a1 : mx;
+        mx = a2 > mx ? a2 : mx;
+        mx = a3 > mx ? a3 : mx;
+      }
+      const double tiny = 1e-12 * rt::wmax(mx);
+      const double s1 = fabs(psi_so1), s2 = fabs(res_b1), s3 = fabs(res_n1);
+      if ((s1 > 0 && s1 < tiny) || (s2 > 0 && s2 < tiny) || (s3 > 0 && s3 < tiny)) status |= PMOC_ST_NOISE_SWITCH;
     }
   };
 
