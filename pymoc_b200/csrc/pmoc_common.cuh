@@ -44,7 +44,7 @@ struct SmemPlan {
   int off_dzu, off_rdzu, off_dzc, off_rdzc;                        // per block, bit-faithful step only
   int off_warp0, per_warp;                                          // per warp region
   int w_col[2];                                                     // column tables of basin / north (4*nzp each)
-  int w_ctop, w_crinv, w_cu, w_psib, w_bs, w_sinv, w_tau, w_bvp;
+  int w_remap, w_psib, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
@@ -77,11 +77,9 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   int w = 0;
   s.w_col[0] = w; w += 4 * s.nzp;
   if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += 4 * s.nzp; }
-  if (flags & PMOC_ISO) {
-    s.w_ctop = w; w += s.nzp;
-    s.w_crinv = w; w += s.nzp;
-    s.w_cu = w; w += s.nzp;
-    if (!exact) { s.w_psib = w; w += s.nbp; }
+  if ((flags & PMOC_ISO) && !exact) {
+    s.w_remap = w; w += 6 * s.nzp;
+    s.w_psib = w; w += s.nbp;
   }
   if (flags & PMOC_HAS_SO) {
     s.w_bs = w; w += s.nyp;
@@ -90,13 +88,14 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     if (flags & PMOC_SO_BVP) { s.w_bvp = w; w += 4 * s.nzp; }
   }
   if (exact) {
-    const int r0 = w;
-    s.w_psib = w;  // live only inside a refresh
+    // the remap scratch (6*nzp + nb, live only inside a refresh) overlays the per-step arrays,
+    // which are rebuilt at the end of every refresh
+    s.w_remap = w;
     s.w_nweff[0] = w; w += 2 * s.nzp;
     s.w_nweff[1] = w; w += 2 * s.nzp;
     s.w_bb = w; w += s.nzp;
     s.w_pm = w; w += s.nzp;
-    if (w - r0 < s.nbp) w = r0 + s.nbp;
+    s.w_psib = w; w += s.nbp;
     s.w_scan = w; w += 10 * 32;
   }
   s.per_warp = w;

@@ -371,20 +371,37 @@ struct BGrid {
   PM_DEV double at(int i) const { return i == nb - 1 ? hi : (double)i * step + lo; }
 };
 
-// Upwind isopycnal remap (psi_thermwind.py:170-185).  Cell data go to shared memory
-// (ctop/crinv/cu, natural order), every lane then owns KB classes of bgrid per pass and sweeps
-// all cells:  psib[i] = sum_c clip((top_c - bgrid_i)/(top_c - bot_c), 0, 1) * u_c.
-// The divide is by a per-cell reciprocal (same +-inf / NaN outcomes for flat cells);
-// the comparisons-based clip keeps NaN like np.clip.
+// Upwind isopycnal remap (psi_thermwind.py:170-185):
+//   psib[i] = sum_c clip((top_c - bgrid_i)/(top_c - bot_c), 0, 1) * u_c,   u_c = -(Psi[c+1]-Psi[c]),
+// cell c taking its bottom/top buoyancy from column 2 where u_c < 0 and from column 1 otherwise.
+//
+// Fast path (both profiles non-decreasing, which stable stratification and the convective
+// adjustment maintain): for a class value x the cells of column X split into "entirely above
+// x" (clip = 1), "entirely below" (clip = 0) and at most one straddling cell, so
+//   psib(x) = sum_X [ S_X[k] + (bX[k] - x) * w_X[k-1] ],   k = #{levels with bX < x},
+// with S_X[k] = sum_{c >= k} [cell c uses X] u_c (a warp suffix scan) and
+// w_X[c] = [cell c uses X] u_c / (bX[c+1] - bX[c]).  O(nb + nz) instead of O(nb nz); the sum is
+// associated differently from np.sum (relative difference ~1e-16).  Flat cells keep the
+// reference's inf/NaN outcomes: (top-x)/0 is +inf -> 1 below the cell, -inf -> 0
+// above it and 0/0 = NaN on it.  Anything else (an inverted cell, a NaN) takes the direct path.
+// Scratch: rs = 6*nzp doubles, psib_s = nb doubles, both owned by this warp.
 template <int LPL>
 PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const double (&b2)[LPL], int nz, int nb,
-                     double* ctop, double* crinv, double* cu, double* psib_s) {
+                     double* rs, double* psib_s) {
+  const int nzp = 32 * LPL, L = rt::lane();
   const double psin = rt::shfl_down(psi[0], 1);
   const double b1n = rt::shfl_down(b1[0], 1), b2n = rt::shfl_down(b2[0], 1);
   double lo = INFINITY, hi = -INFINITY;
+  double u[LPL], up1[LPL], up2[LPL];
+  bool unsorted = false;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
+    const bool last = j == LPL - 1;
+    const int jn = j + 1 < LPL ? j + 1 : j;
+    up1[j] = last ? b1n : b1[jn];
+    up2[j] = last ? b2n : b2[jn];
+    u[j] = 0.0;
     if (i < nz) {
       lo = b1[j] < lo ? b1[j] : lo;
       lo = b2[j] < lo ? b2[j] : lo;
@@ -392,15 +409,8 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       hi = b2[j] > hi ? b2[j] : hi;
     }
     if (i < nz - 1) {
-      const bool last = j == LPL - 1;
-      const int jn = j + 1 < LPL ? j + 1 : j;
-      const double u = -((last ? psin : psi[jn]) - psi[j]);
-      const bool from2 = u < 0;
-      const double bot = from2 ? b2[j] : b1[j];
-      const double top = from2 ? (last ? b2n : b2[jn]) : (last ? b1n : b1[jn]);
-      ctop[i] = top;
-      crinv[i] = 1.0 / (top - bot);
-      cu[i] = u;
+      u[j] = -((last ? psin : psi[jn]) - psi[j]);
+      unsorted |= !(up1[j] >= b1[j]) || !(up2[j] >= b2[j]) || u[j] != u[j];
     }
   }
   BGrid G;
@@ -408,9 +418,107 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
   G.hi = rt::wmax(hi);
   G.nb = nb;
   G.step = (G.hi - G.lo) / (double)(nb - 1);
+  if (rt::ballot(unsorted) == 0) {
+    double *b1_s = rs, *b2_s = rs + nzp, *w1_s = rs + 2 * nzp, *w2_s = rs + 3 * nzp, *S1_s = rs + 4 * nzp,
+           *S2_s = rs + 5 * nzp;
+    // suffix sums of the transports taken from each column
+    double s1[LPL], s2[LPL];
+    double r1 = 0.0, r2 = 0.0;
+    PM_UNROLL
+    for (int j = LPL - 1; j >= 0; --j) {
+      const bool from2 = u[j] < 0;
+      r1 = r1 + (from2 ? 0.0 : u[j]);
+      r2 = r2 + (from2 ? u[j] : 0.0);
+      s1[j] = r1;
+      s2[j] = r2;
+    }
+    double t1 = r1, t2 = r2;  // inclusive suffix over lanes
+    PM_UNROLL
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o1 = rt::shfl_down(t1, d), o2 = rt::shfl_down(t2, d);
+      if (L + d < 32) {
+        t1 = t1 + o1;
+        t2 = t2 + o2;
+      }
+    }
+    const double e1 = t1 - r1, e2 = t2 - r2;  // lanes above this one
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const int i = lev<LPL>(j);
+      if (i < nz) {
+        const bool cell = i < nz - 1, from2 = u[j] < 0;
+        b1_s[i] = b1[j];
+        b2_s[i] = b2[j];
+        S1_s[i] = s1[j] + e1;
+        S2_s[i] = s2[j] + e2;
+        w1_s[i] = (cell && !from2) ? u[j] / (up1[j] - b1[j]) : 0.0;
+        w2_s[i] = (cell && from2) ? u[j] / (up2[j] - b2[j]) : 0.0;
+      }
+    }
+    rt::syncwarp();
+    const int cpl = (nb + 31) >> 5;  // classes per lane, contiguous
+    const int i0 = L * cpl, i1 = i0 + cpl < nb ? i0 + cpl : nb;
+    int k1 = 0, k2 = 0;
+    if (i0 < nb) {  // first index with bX >= x for the lane's first class
+      const double x = G.at(i0);
+      int a = 0, b = nz;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (b1_s[mid] < x) a = mid + 1; else b = mid;
+      }
+      k1 = a;
+      a = 0; b = nz;
+      while (a < b) {
+        const int mid = (a + b) >> 1;
+        if (b2_s[mid] < x) a = mid + 1; else b = mid;
+      }
+      k2 = a;
+    }
+    rt::syncwarp();
+    double held = 0.0;  // results leave in a second sweep: psib_s may overlay nothing of rs, but keep reads first
+    for (int i = i0; i < i1; ++i) {
+      const double x = G.at(i);
+      while (k1 < nz && b1_s[k1] < x) ++k1;
+      while (k2 < nz && b2_s[k2] < x) ++k2;
+      double c1 = 0.0, c2 = 0.0;
+      if (k1 < nz) {
+        const double bk = b1_s[k1];
+        c1 = S1_s[k1];
+        if (k1 > 0 && bk != x) c1 = c1 + (bk - x) * w1_s[k1 - 1];
+        if (bk == x)  // flat cells sitting exactly on the class: 0/0 in the reference
+          for (int c = k1; c + 1 < nz && b1_s[c + 1] == x; ++c)
+            if (w1_s[c] != 0.0) c1 = NAN;
+      }
+      if (k2 < nz) {
+        const double bk = b2_s[k2];
+        c2 = S2_s[k2];
+        if (k2 > 0 && bk != x) c2 = c2 + (bk - x) * w2_s[k2 - 1];
+        if (bk == x)
+          for (int c = k2; c + 1 < nz && b2_s[c + 1] == x; ++c)
+            if (w2_s[c] != 0.0) c2 = NAN;
+      }
+      held = c1 + c2;
+      psib_s[i] = held;
+    }
+    rt::syncwarp();
+    return G;
+  }
+  // direct path: every class against every cell
+  double *ctop = rs, *crinv = rs + nzp, *cu = rs + 2 * nzp;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz - 1) {
+      const bool from2 = u[j] < 0;
+      const double bot = from2 ? b2[j] : b1[j];
+      const double top = from2 ? up2[j] : up1[j];
+      ctop[i] = top;
+      crinv[i] = 1.0 / (top - bot);
+      cu[i] = u[j];
+    }
+  }
   rt::syncwarp();
   constexpr int KB = 8;
-  const int L = rt::lane();
   for (int base = 0; base < nb; base += 32 * KB) {
     double bg[KB], acc[KB];
     PM_UNROLL
@@ -420,13 +528,13 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       acc[k] = 0.0;
     }
     for (int c = 0; c < nz - 1; ++c) {
-      const double top = ctop[c], r = crinv[c], u = cu[c];
+      const double top = ctop[c], r = crinv[c], uc = cu[c];
       PM_UNROLL
       for (int k = 0; k < KB; ++k) {
         double t = (top - bg[k]) * r;
         t = t < 0. ? 0. : t;
         t = t > 1. ? 1. : t;
-        acc[k] = rt::fma(t, u, acc[k]);
+        acc[k] = rt::fma(t, uc, acc[k]);
       }
     }
     PM_UNROLL
@@ -897,11 +1005,9 @@ PM_DEV int search_guess(double key, const double* arr, int len, int guess) {
   return imin - 1;
 }
 
-// one query of np.interp(x, xp, fp) the way arr_interp evaluates it; *j is the carried guess
-PM_DEV double interp_np(double x, const double* xp, const double* fp, int n, int* j) {
+// value of np.interp(x, xp, fp) once arr_interp's search has returned index k
+PM_DEV double interp_at(double x, const double* xp, const double* fp, int n, int k) {
   if (x != x) return x;
-  const int k = search_guess(x, xp, n, *j);
-  *j = k;
   if (k == -1) return fp[0];
   if (k == n) return fp[n - 1];
   if (k == n - 1) return fp[k];
@@ -917,6 +1023,7 @@ PM_DEV double interp_np(double x, const double* xp, const double* fp, int n, int
 
 struct MlState {
   double bs[kMLP];                            // surface buoyancy of the lane's points
+  int jp[kMLP];                               // np.interp search results of the previous step (predictions)
   double ps[kMLP];                            // Psi_s of the last step (diagnostic)
   double a[kMLP], m[kMLP];                    // Thomas factors of U = tridiag(-s/2, 1+s, -s/2)
   double sfh[kMLP], rv[kMLP], brest[kMLP];    // surflux/h, rest_mask*v_pist/h, b_rest
@@ -955,6 +1062,7 @@ PM_DEV void ml_setup(MlState& S, const double* ygrid, int ny, double Ks, double 
     S.a[e] = 0.0;
     S.m[e] = in ? 1.0 : 0.0;  // identity rows (first, last); padding contributes nothing
     S.ps[e] = 0.0;
+    S.jp[e] = 0;
   }
   double aprev = 0.0;
   for (int i = 1; i < ny - 1; ++i) {
@@ -1039,14 +1147,29 @@ PM_DEV void ml_step(MlState& S, const double* bb_s, const double* pm_s, int nz, 
     for (int e = 0; e < kMLP; ++e)
       if (mlk(e) < ny) ps[e] = interp1(S.bs[e], bb_s, pm_s, nz);
   } else {
-    *status |= 8u;  // PMOC_ST_XP_NONMONOTONE: the guess-carrying search decides, as in numpy
-    int j = 0;
-    for (int k = 0; k < ny; ++k) {
-      const double v = interp_np(bs_s[k], bb_s, pm_s, nz, &j);
-      PM_UNROLL
-      for (int e = 0; e < kMLP; ++e)
-        if (mlk(e) == k) ps[e] = v;
+    // PMOC_ST_XP_NONMONOTONE: numpy's search carries its result into the next query as the guess
+    // (j_k = search_guess(x_k, j_{k-1}), j_{-1} = 0), and for an unsorted abscissa the answer depends
+    // on it.  The chain is evaluated speculatively: every lane searches with the guess its
+    // predecessor produced in the previous time step, then the guesses actually used are compared
+    // with the results actually obtained and the pass repeats until they agree -- which is exactly
+    // the sequential chain (lane 0 is always right, each pass fixes at least one more lane), and
+    // is one pass when the state moves slowly.
+    *status |= 8u;
+    int pred = rt::shfl_i(S.jp[kMLP - 1], Ln > 0 ? Ln - 1 : 0);
+    int j0 = 0, j1 = 0;
+    for (int pass = 0; pass < 33; ++pass) {
+      const int g0 = Ln == 0 ? 0 : pred;
+      j0 = (mlk(0) < ny && S.bs[0] == S.bs[0]) ? search_guess(S.bs[0], bb_s, nz, g0) : g0;
+      j1 = (mlk(1) < ny && S.bs[1] == S.bs[1]) ? search_guess(S.bs[1], bb_s, nz, j0) : j0;
+      const int got = rt::shfl_i(j1, Ln > 0 ? Ln - 1 : 0);
+      const bool bad = Ln > 0 && got != pred;
+      pred = got;
+      if (rt::ballot(bad) == 0) break;
     }
+    S.jp[0] = j0;
+    S.jp[1] = j1;
+    if (mlk(0) < ny) ps[0] = interp_at(S.bs[0], bb_s, pm_s, nz, j0);
+    if (mlk(1) < ny) ps[1] = interp_at(S.bs[1], bb_s, pm_s, nz, j1);
   }
   const int amin = ml_argmin(S);
   PM_UNROLL

@@ -139,8 +139,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       if (write && M.Psi_tw) pm::store_lev<LPL>(psi_tw, M.Psi_tw + m * nz, nz);
       if (ISO) {
         double* psib_s = ws + sp.w_psib;
-        const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_ctop, ws + sp.w_crinv,
-                                              ws + sp.w_cu, psib_s);
+        const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_remap, psib_s);
         PM_UNROLL
         for (int j = 0; j < LPL; ++j) {
           const bool ok = pm::lev<LPL>(j) < nz;

@@ -74,13 +74,13 @@ PM_GLOBAL void k_psib(ThermwindArgs a) {
   const int nz = a.nz, nb = a.nb, L = rt::lane(), W = rt::warp_in_block();
   const long long m = rt::block_idx() * rt::warps_per_block() + W;
   if (m >= a.M) return;
-  double* ws = rt::smem() + (size_t)(3 * a.nzp + a.nbp) * W;
+  double* ws = rt::smem() + (size_t)(6 * a.nzp + a.nbp) * W;
   double b1[LPL], b2[LPL], psi[LPL];
   pm::load_lev<LPL>(b1, vrow(a.b1, m), nz, 0.0);
   pm::load_lev<LPL>(b2, vrow(a.b2, m), nz, 0.0);
   pm::load_lev<LPL>(psi, vrow(a.Psi_in, m), nz, 0.0);
-  double* psib_s = ws + 3 * a.nzp;
-  const pm::BGrid G = pm::tw_psib<LPL>(psi, b1, b2, nz, nb, ws, ws + a.nzp, ws + 2 * a.nzp, psib_s);
+  double* psib_s = ws + 6 * a.nzp;
+  const pm::BGrid G = pm::tw_psib<LPL>(psi, b1, b2, nz, nb, ws, psib_s);
   for (int i = L; i < nb; i += 32) {
     a.psib[m * nb + i] = psib_s[i];
     if (a.bgrid) a.bgrid[m * nb + i] = G.at(i);
@@ -359,7 +359,7 @@ int pmoc_thermwind_psib(int64_t M, int32_t nz, int32_t nb, pmoc_vec Psi, pmoc_ve
   PM_DISPATCH_LPL(nz, {
     a.nzp = 32 * LPL;
     return launch(k_psib<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
-                  sizeof(double) * (size_t)(3 * a.nzp + a.nbp) * kWarpsPerBlock, stream, a);
+                  sizeof(double) * (size_t)(6 * a.nzp + a.nbp) * kWarpsPerBlock, stream, a);
   });
   return PMOC_OK;
 }

@@ -230,3 +230,52 @@ def ml_checks():
       ml.timestep(b_basin=inp['b_basin'], Psi_b=inp['Psi_b'], dt=inp['dt'])
       assert relmax(ml.Psi_s, out['Psi_s'][step]) < TOL, (i, step, relmax(ml.Psi_s, out['Psi_s'][step]))
       assert relmax(ml.bs, out['bs'][step]) < TOL, (i, step, relmax(ml.bs, out['bs'][step]))
+
+
+# ---------------------------------------------------- isopycnal remap: fast and direct paths
+def psib_edge_cases():
+  """Psib / Psibz against the live oracle on profiles that steer the kernel through its O(nb+nz) path
+  (non-decreasing columns, flat cells, flat cells sitting exactly on a class = the reference's 0/0)
+  and its direct path (inverted cells), SURVEY H3."""
+  from oracle import pymoc_oracle as O
+  rng = np.random.default_rng(1)
+
+  def check(tag, z, b1, b2, psi, nb=500, want_nan=None):
+    with np.errstate(all='ignore'):
+      want_p, want_g = O.thermwind_psib(psi, b1, b2, nb)
+      wb, wn, _, _ = O.thermwind_psibz(psi, b1, b2, nb)
+    tw = Psi_Thermwind(z=z, b1=b1.copy(), b2=b2.copy())
+    tw.Psi = psi.copy()
+    got = tw.Psib(nb)
+    iso = tw.Psibz(nb)
+    assert relmax(tw.bgrid, want_g) == 0.0, tag
+    for g, w, key in ((got, want_p, 'psib'), (iso[0], wb, 'iso_b'), (iso[1], wn, 'iso_n')):
+      assert relmax(g, w) < TOL, (tag, key, relmax(g, w))
+    if want_nan is not None:
+      assert int(np.isnan(want_p).sum()) == want_nan, (tag, int(np.isnan(want_p).sum()))
+
+  for nz in (46, 80, 200):
+    z = np.linspace(-4000, 0, nz)
+    b1, b2 = 0.03 * np.exp(z / 300.), 0.004 * np.exp(z / 300.)
+    psi = 10 * np.sin(np.pi * z / 4000.)**2 * np.sign(z + 1500)
+    psi[0] = psi[-1] = 0
+    check('monotone', z, b1, b2, psi)
+    check('monotone nb=37', z, b1, b2, psi, 37)
+    check('monotone nb=1000', z, b1, b2, psi, 1000)
+    check('b2 flat zero', z, b1 - 0.001, 0 * z, psi)
+    check('b2 flat on bgrid[0]', z, b1, 0 * z + b1.min(), psi, want_nan=1)
+    c = b1.copy(); c[0] = c[1]
+    check('flat bottom cell', z, c, b2, psi)
+    c = b1.copy(); c[5:9] = c[5]
+    check('flat run, down', z, c, b2, -np.abs(psi))
+    check('flat run, up', z, c, b2, np.abs(psi))
+    c = b2.copy(); c[0] = np.nextafter(c[1], 1.0)
+    check('bottom cell inverted by one ulp', z, b1, c, psi)
+    c = b1.copy(); c[10:20] = c[10:20][::-1]
+    check('inverted region', z, c, b2, psi)
+    pr = np.cumsum(rng.normal(size=nz)); pr[0] = 0
+    check('random sorted', z, np.sort(rng.uniform(0, 0.03, nz)), np.sort(rng.uniform(0, 0.01, nz)), pr)
+    ba = np.linspace(0, 0.03, nz)
+    check('classes on the levels', z, ba, 0.5 * ba, pr, nb=nz)
+    c = ba.copy(); c[7] = c[8]
+    check('flat cell on a class', z, c, 0.5 * ba, pr, nb=nz)

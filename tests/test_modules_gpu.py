@@ -38,3 +38,7 @@ def test_so():
 
 def test_ml():
   mc.ml_checks()
+
+
+def test_psib_edge_cases():
+  mc.psib_edge_cases()
