@@ -82,17 +82,25 @@ def _cpu_task(args):
   return time.perf_counter() - t0
 
 
-def cpu_reference(workload, M, nsteps, tasks_per_core=2, cores=None):
+def cpu_reference(workload, M, nsteps=0, tasks_per_core=2, cores=None, target_s=15.0):
   """Reference-faithful CPU loop (the oracle in its default modes: solve_bvp, brentq, dense inv
-  exactly where the reference calls them) on all host cores; returns member-steps/s."""
+  exactly where the reference calls them) on all host cores; returns member-steps/s.  With
+  ``nsteps == 0`` the steps per task are sized from a short pilot so that the sample takes about
+  ``target_s`` seconds of wall time (a bounded sample of the same workload)."""
   import multiprocessing as mp
   cores = cores or os.cpu_count() or 1
   ntask = cores * tasks_per_core
   members = [int(i * (M - 1) / max(ntask - 1, 1)) for i in range(ntask)]
-  jobs = [(workload, M, m, nsteps) for m in members]
+  K = WORKLOADS[workload][0](min(M, 64)).K
   ctx = mp.get_context('spawn')
   with ctx.Pool(cores) as pool:
-    pool.map(_cpu_task, [(workload, M, 0, 2)] * cores)  # import + warm-up, untimed
+    pilot_steps = 2 * K + 1
+    t_pilot = max(pool.map(_cpu_task, [(workload, M, m, pilot_steps) for m in members[:cores]]))  # import + warm-up
+    if nsteps <= 0:
+      per_step = t_pilot / pilot_steps
+      nsteps = int(max(pilot_steps, min(200000, target_s / (per_step * tasks_per_core))))
+      nsteps = max(K, (nsteps // K) * K) + 1
+    jobs = [(workload, M, m, nsteps) for m in members]
     t0 = time.perf_counter()
     pool.map(_cpu_task, jobs, chunksize=1)
     wall = time.perf_counter() - t0
@@ -295,10 +303,10 @@ def reference_arm(args):
   spec = build(min(M, 65536))
   vals = []
   for _ in range(args.warmup):
-    cpu_reference(args.workload, min(M, 65536), max(args.cpu_steps // 4, 1), tasks_per_core=1)
+    cpu_reference(args.workload, min(M, 65536), args.cpu_steps, tasks_per_core=1, target_s=4.0)
   t0 = time.perf_counter()
   for _ in range(args.steps):
-    v, cores, sample, wall = cpu_reference(args.workload, min(M, 65536), args.cpu_steps, tasks_per_core=1)
+    v, cores, sample, wall = cpu_reference(args.workload, min(M, 65536), args.cpu_steps, tasks_per_core=1, target_s=12.0)
     vals.append(v)
   total = time.perf_counter() - t0
   value = float(np.mean(vals))
@@ -323,7 +331,7 @@ def main():
   ap.add_argument('--members', type=int, default=0, help='members per GPU (default: workload size)')
   ap.add_argument('--nt', type=int, default=0, help='model time steps per bench step')
   ap.add_argument('--e2e-steps', type=int, default=3)
-  ap.add_argument('--cpu-steps', type=int, default=720, help='model steps per CPU-baseline task')
+  ap.add_argument('--cpu-steps', type=int, default=0, help='model steps per CPU-baseline task (0: sized for ~15 s)')
   ap.add_argument('--no-cpu', action='store_true')
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

@@ -40,8 +40,8 @@ def c1_timestepping(M=1, nz=70):
   b0 = bs * np.exp(z / 300.) + bbot
   if M == 1:
     kappa, sweep = kap(z), {}
-  else:  # scale the diffusivity profile
-    sweep = lattice(kapfac=np.linspace(0.5, 2.0, M))
+  else:  # scale the diffusivity profile (dt = 60 d is diffusively stable up to kapfac ~ 1.37)
+    sweep = lattice(kapfac=np.linspace(0.5, 1.25, M))
     kappa = sweep['kapfac'][:, None] * kap(z)[None, :]
   return ModelSpec(
       M=M, z=z, dt=60 * DAY, K=1, name='C1 example_timestepping', sweep=sweep,

@@ -42,9 +42,10 @@ struct SmemPlan {
   int nzp, nyp, nbp;
   int off_zs, off_zl, off_rdu, off_rdd, off_ruu, off_rdd2, off_y;  // per block
   int off_dzu, off_rdzu, off_dzc, off_rdzc;                        // per block, bit-faithful step only
+  int off_tap;                                                      // per block, 4*nzp Psi_SO tapers
   int off_warp0, per_warp;                                          // per warp region
   int w_col[2];                                                     // column tables of basin / north (4*nzp each)
-  int w_remap, w_psib, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
+  int w_remap, w_psib, w_cnt, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
@@ -73,6 +74,7 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     s.off_rdzc = o; o += s.nzp;
   }
   s.off_y = o; o += s.nyp;
+  if (flags & PMOC_HAS_SO) { s.off_tap = o; o += 4 * s.nzp; }
   s.off_warp0 = o;
   int w = 0;
   s.w_col[0] = w; w += 4 * s.nzp;
@@ -80,6 +82,7 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   if ((flags & PMOC_ISO) && !exact) {
     s.w_remap = w; w += 6 * s.nzp;
     s.w_psib = w; w += s.nbp;
+    s.w_cnt = w; w += s.nbp / 2 + 2;
   }
   if (flags & PMOC_HAS_SO) {
     s.w_bs = w; w += s.nyp;
@@ -96,6 +99,7 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     s.w_bb = w; w += s.nzp;
     s.w_pm = w; w += s.nzp;
     s.w_psib = w; w += s.nbp;
+    s.w_cnt = w; w += s.nbp / 2 + 2;
     s.w_scan = w; w += 10 * 32;
   }
   s.per_warp = w;

@@ -371,6 +371,20 @@ struct BGrid {
   PM_DEV double at(int i) const { return i == nb - 1 ? hi : (double)i * step + lo; }
 };
 
+// number of classes with bgrid value <= v (index estimated by division, then corrected against
+// the actual grid values)
+PM_DEV int bgrid_count_le(const BGrid& G, double v) {
+  const int nb = G.nb;
+  if (v < G.lo) return 0;
+  if (v >= G.hi) return nb;
+  if (!(G.step > 0.)) return v >= G.lo ? nb : 0;
+  const double r = (v - G.lo) / G.step;
+  int p = r < (double)(nb - 1) ? (int)r + 1 : nb;
+  while (p < nb && G.at(p) <= v) ++p;
+  while (p > 0 && G.at(p - 1) > v) --p;
+  return p;
+}
+
 // Upwind isopycnal remap (psi_thermwind.py:170-185):
 //   psib[i] = sum_c clip((top_c - bgrid_i)/(top_c - bot_c), 0, 1) * u_c,   u_c = -(Psi[c+1]-Psi[c]),
 // cell c taking its bottom/top buoyancy from column 2 where u_c < 0 and from column 1 otherwise.
@@ -384,10 +398,14 @@ struct BGrid {
 // associated differently from np.sum (relative difference ~1e-16).  Flat cells keep the
 // reference's inf/NaN outcomes: (top-x)/0 is +inf -> 1 below the cell, -inf -> 0
 // above it and 0/0 = NaN on it.  Anything else (an inverted cell, a NaN) takes the direct path.
-// Scratch: rs = 6*nzp doubles, psib_s = nb doubles, both owned by this warp.
+// k is not searched for: every level drops a count into the class slot where its buoyancy first
+// falls below the class value (integer shared-memory atomics: exact, order independent), and a
+// prefix sum over the classes turns the counts into k for both columns at once.
+// Scratch: rs = 6*nzp doubles, psib_s = nb doubles, cnt_s = nb+1 ints, all owned by this warp.
+
 template <int LPL>
 PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const double (&b2)[LPL], int nz, int nb,
-                     double* rs, double* psib_s) {
+                     double* rs, double* psib_s, int* cnt_s) {
   const int nzp = 32 * LPL, L = rt::lane();
   const double psin = rt::shfl_down(psi[0], 1);
   const double b1n = rt::shfl_down(b1[0], 1), b2n = rt::shfl_down(b2[0], 1);
@@ -456,30 +474,31 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       }
     }
     rt::syncwarp();
-    const int cpl = (nb + 31) >> 5;  // classes per lane, contiguous
-    const int i0 = L * cpl, i1 = i0 + cpl < nb ? i0 + cpl : nb;
-    int k1 = 0, k2 = 0;
-    if (i0 < nb) {  // first index with bX >= x for the lane's first class
-      const double x = G.at(i0);
-      int a = 0, b = nz;
-      while (a < b) {
-        const int mid = (a + b) >> 1;
-        if (b1_s[mid] < x) a = mid + 1; else b = mid;
+    for (int i = L; i <= nb; i += 32) cnt_s[i] = 0;
+    rt::syncwarp();
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      if (lev<LPL>(j) < nz) {
+        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, b1[j])], 1);
+        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, b2[j])], 1 << 16);
       }
-      k1 = a;
-      a = 0; b = nz;
-      while (a < b) {
-        const int mid = (a + b) >> 1;
-        if (b2_s[mid] < x) a = mid + 1; else b = mid;
-      }
-      k2 = a;
     }
     rt::syncwarp();
-    double held = 0.0;  // results leave in a second sweep: psib_s may overlay nothing of rs, but keep reads first
+    const int cpl = (nb + 31) >> 5;  // classes per lane, contiguous
+    const int i0 = L * cpl < nb ? L * cpl : nb, i1 = i0 + cpl < nb ? i0 + cpl : nb;
+    int run = 0;
+    for (int i = i0; i < i1; ++i) run += cnt_s[i];
+    int incl = run;
+    PM_UNROLL
+    for (int d = 1; d < 32; d <<= 1) {
+      const int o = rt::shfl_i(incl, L >= d ? L - d : L);
+      if (L >= d) incl += o;
+    }
+    run = incl - run;  // levels counted in the classes of the lanes below
     for (int i = i0; i < i1; ++i) {
       const double x = G.at(i);
-      while (k1 < nz && b1_s[k1] < x) ++k1;
-      while (k2 < nz && b2_s[k2] < x) ++k2;
+      run += cnt_s[i];
+      const int k1 = run & 0xffff, k2 = run >> 16;  // #{levels with bX < x}
       double c1 = 0.0, c2 = 0.0;
       if (k1 < nz) {
         const double bk = b1_s[k1];
@@ -497,8 +516,7 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
           for (int c = k2; c + 1 < nz && b2_s[c + 1] == x; ++c)
             if (w2_s[c] != 0.0) c2 = NAN;
       }
-      held = c1 + c2;
-      psib_s[i] = held;
+      psib_s[i] = c1 + c2;
     }
     rt::syncwarp();
     return G;
@@ -699,7 +717,7 @@ PM_DEV double mean100(double tau) {
 
 struct SoPar {
   double tau_ave, f, rho, L, KGM, smax;
-  const double *sill, *ektap, *toptap, *bottap;  // [nz] natural order, global
+  const double *sill, *ektap, *toptap, *bottap;  // taper profiles, lane-major (shared memory)
   const double* tau_y;                           // tau on the y grid (shared memory) or nullptr for a float tau
   double c;                                      // F2010 phase speed (BVP branch only)
   int with_Ek;
@@ -710,6 +728,21 @@ struct SoSurf {  // per-refresh scan of bs(y)
   int south;
   bool mono;
 };
+// block-cooperative copy of the four host-evaluated taper profiles into lane-major shared memory
+template <int LPL>
+PM_DEV void taper_fill(double* dst, const double* PM_RESTRICT sill, const double* PM_RESTRICT ektap,
+                       const double* PM_RESTRICT toptap, const double* PM_RESTRICT bottap, int nz, int tid, int nthr) {
+  const int nzp = 32 * LPL;
+  for (int s = tid; s < nzp; s += nthr) {
+    const int i = (s & 31) * LPL + (s >> 5);
+    const bool in = i < nz;
+    dst[s] = in ? sill[i] : 0.0;
+    dst[nzp + s] = in ? ektap[i] : 0.0;
+    dst[2 * nzp + s] = in ? toptap[i] : 0.0;
+    dst[3 * nzp + s] = in ? bottap[i] : 0.0;
+  }
+}
+
 // Scan of the surface buoyancy: minimum / argmin (first occurrence, np.argmin), monotonicity
 // north of it, and the inverse segment slopes.  Warp-cooperative; redone only when bs changes.
 PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int ny) {
@@ -891,48 +924,98 @@ PM_DEV void so_bvp(double (&g)[LPL], const double (&b)[LPL], double c, double ya
   rt::syncwarp();
 }
 
+// ys(b) for all levels of the lane at once when bs(y) is non-decreasing north of its minimum
+// (outcrop_monotone, but branch-free with a fixed trip count so that the LPL searches overlap)
+template <int LPL>
+PM_DEV void outcrop_monotone_all(double (&yo)[LPL], const double (&b)[LPL], const double* ygrid, const double* bs,
+                                 const double* sinv, int ny, const SoSurf& S) {
+  int lo[LPL], hi[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    lo[j] = S.south;
+    hi[j] = ny - 1;
+  }
+  int span = ny - 1 - S.south, trips = 0;
+  while ((1 << trips) < span) ++trips;
+  for (int it = 0; it < trips; ++it) {
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const int mid = (lo[j] + hi[j]) >> 1;
+      const bool open = hi[j] - lo[j] > 1, ge = bs[mid] >= b[j];
+      hi[j] = (open && ge) ? mid : hi[j];
+      lo[j] = (open && !ge) ? mid : lo[j];
+    }
+  }
+  const double bsS = bs[S.south], yS = ygrid[S.south];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int h = hi[j];
+    double y = ygrid[h - 1] + (b[j] - bs[h - 1]) * sinv[h - 1];
+    if (bs[h] == b[j]) y = ygrid[h];
+    if (S.bsN == b[j]) y = S.yN;
+    if (bsS == b[j]) y = yS;
+    if (b[j] > S.bsN) y = S.yN;
+    if (b[j] < S.mn) y = S.y0 - 1e3;
+    yo[j] = y;
+  }
+}
+
 // Psi_SO.solve (psi_SO.py:106-140, 218-243, 302-354): outcrop latitudes, Ekman transport, GM
-// transport with the explicit slope clip or (BVP) the F2010 smoother.  Sv.
+// transport with the explicit slope clip or (BVP) the F2010 smoother.  Sv.  The four taper
+// profiles are read lane-major (slot lm(j)) from P.sill/ektap/toptap/bottap.
 template <int LPL, bool BVP = false>
 PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], double (&ysv)[LPL],
                      const double (&b)[LPL], const double* ygrid, const double* bs, const double* sinv, int ny,
                      const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status) {
-  if (!S.mono) *status |= 2u;
   const double pre0 = P.tau_ave / P.f / P.rho * P.L;
   const double c6 = 1e6, r6 = 1.0 / 1e6;
+  if (S.mono && S.south < ny - 1) {
+    outcrop_monotone_all<LPL>(ysv, b, ygrid, bs, sinv, ny, S);
+  } else {
+    if (!S.mono) *status |= 2u;
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const double bi = b[j];
+      double yo = 0.;
+      if (lev<LPL>(j) < nz) {
+        if (bi < S.mn)
+          yo = S.y0 - 1e3;
+        else if (bi > S.bsN)
+          yo = S.yN;
+        else if (S.mono)
+          yo = outcrop_monotone(bi, ygrid, bs, sinv, ny, S.south);
+        else {
+          bool bad = false;
+          yo = outcrop_brent(bi, ygrid, bs, ny, S.south, &bad);
+          if (bad) *status |= 4u;
+        }
+      }
+      ysv[j] = yo;
+    }
+  }
   double dyv[LPL];
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
-    const int i = lev<LPL>(j);
-    double e = 0., g = 0., yo = 0., dy = 1.;
-    if (i < nz) {
-      const double bi = b[j];
-      if (bi < S.mn)
-        yo = S.y0 - 1e3;
-      else if (bi > S.bsN)
-        yo = S.yN;
-      else if (S.mono)
-        yo = outcrop_monotone(bi, ygrid, bs, sinv, ny, S.south);
-      else {
-        bool bad = false;
-        yo = outcrop_brent(bi, ygrid, bs, ny, S.south, &bad);
-        if (bad) *status |= 4u;
-      }
-      const double pre = P.tau_y ? tau_mean100(yo, S.yN, ygrid, P.tau_y, ny) / P.f / P.rho * P.L : pre0;
-      e = div_const(pre * P.sill[i] * P.ektap[i], c6, r6);
-      dy = S.yN - yo;
-      dy = 0.1 > dy ? 0.1 : dy;
-      if (BVP) {
-        g = P.KGM * zs[i] / dy * P.L * P.toptap[i] * P.bottap[i];
-      } else {
-        const double s = zs[i] / dy, ms = -P.smax;
-        const double mx = (s >= ms || s != s) ? s : ms;
-        g = P.KGM * mx * P.L * P.toptap[i] * P.bottap[i];
-      }
+    const int i = lev<LPL>(j), s = lm(j);
+    const bool in = i < nz;
+    const double yo = in ? ysv[j] : 0.0;
+    double pre = pre0;
+    if (P.tau_y != nullptr && in) pre = tau_mean100(yo, S.yN, ygrid, P.tau_y, ny) / P.f / P.rho * P.L;
+    const double e = div_const(pre * P.sill[s] * P.ektap[s], c6, r6);
+    double dy = S.yN - yo;
+    dy = 0.1 > dy ? 0.1 : dy;
+    const double z = zs[i < nz ? i : nz - 1];
+    double g;
+    if (BVP) {
+      g = P.KGM * z / dy * P.L * P.toptap[s] * P.bottap[s];
+    } else {
+      const double sl = z / dy, ms = -P.smax;
+      const double mx = (sl >= ms || sl != sl) ? sl : ms;
+      g = P.KGM * mx * P.L * P.toptap[s] * P.bottap[s];
     }
-    ek[j] = e;
-    gm[j] = g;
-    dyv[j] = dy;
+    ek[j] = in ? e : 0.0;
+    gm[j] = in ? g : 0.0;
+    dyv[j] = in ? dy : 1.0;
     ysv[j] = yo;
   }
   if (BVP) {
@@ -946,17 +1029,15 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
-    double t = gm[j], ps = 0., g = 0.;
-    if (i < nz) {
-      if (dyv[j] > S.yN - S.y0) {
-        const double alt = -ek[j] * 1e6;
-        t = (t >= alt || t != t) ? t : alt;
-      }
-      g = div_const(t, c6, r6);
-      ps = i == 0 ? 0. : ek[j] + g;
+    double t = gm[j];
+    if (dyv[j] > S.yN - S.y0) {
+      const double alt = -ek[j] * 1e6;
+      t = (t >= alt || t != t) ? t : alt;
     }
-    gm[j] = g;
-    psi[j] = ps;
+    const double g = div_const(t, c6, r6);
+    const bool in = i < nz;
+    gm[j] = in ? g : 0.0;
+    psi[j] = (in && i != 0) ? ek[j] + g : 0.0;
   }
 }
 

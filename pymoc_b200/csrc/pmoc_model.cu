@@ -25,8 +25,11 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   if (ML)
     pm::geo_fill_exact<LPL>(sm + sp.off_dzu, sm + sp.off_rdzu, sm + sp.off_dzc, sm + sp.off_rdzc, M.z, nz, W * 32 + L,
                             nthr);
-  if (SO)
+  if (SO) {
     for (int i = W * 32 + L; i < sp.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
+    pm::taper_fill<LPL>(sm + sp.off_tap, M.so_sill_taper, M.so_ek_taper, M.so_top_taper, M.so_bot_taper, nz,
+                        W * 32 + L, nthr);
+  }
   rt::syncblock();
   const pm::GeoTab G = geo_of(sm, sp);
   const double* zs = G.zs;
@@ -73,7 +76,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     so.bvp_s = BVP ? ws + sp.w_bvp : nullptr;
     so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
     so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
-    so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
+    so.sill = sm + sp.off_tap; so.ektap = so.sill + sp.nzp; so.toptap = so.sill + 2 * sp.nzp;
+    so.bottap = so.sill + 3 * sp.nzp;
     const double* src = vrow(M.so_bs, m);
     if (ML) src = M.ml_bs + m * ny;  // the mixed layer's bs (run_JansenNadeau_2018.py:214)
     for (int i = L; i < sp.nyp; i += 32) ws[sp.w_bs + i] = src[i < ny ? i : ny - 1];
@@ -139,7 +143,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       if (write && M.Psi_tw) pm::store_lev<LPL>(psi_tw, M.Psi_tw + m * nz, nz);
       if (ISO) {
         double* psib_s = ws + sp.w_psib;
-        const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_remap, psib_s);
+        const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_remap, psib_s,
+                                              reinterpret_cast<int*>(ws + sp.w_cnt));
         PM_UNROLL
         for (int j = 0; j < LPL; ++j) {
           const bool ok = pm::lev<LPL>(j) < nz;

@@ -74,13 +74,13 @@ PM_GLOBAL void k_psib(ThermwindArgs a) {
   const int nz = a.nz, nb = a.nb, L = rt::lane(), W = rt::warp_in_block();
   const long long m = rt::block_idx() * rt::warps_per_block() + W;
   if (m >= a.M) return;
-  double* ws = rt::smem() + (size_t)(6 * a.nzp + a.nbp) * W;
+  double* ws = rt::smem() + (size_t)(6 * a.nzp + a.nbp + a.nbp / 2 + 2) * W;
   double b1[LPL], b2[LPL], psi[LPL];
   pm::load_lev<LPL>(b1, vrow(a.b1, m), nz, 0.0);
   pm::load_lev<LPL>(b2, vrow(a.b2, m), nz, 0.0);
   pm::load_lev<LPL>(psi, vrow(a.Psi_in, m), nz, 0.0);
   double* psib_s = ws + 6 * a.nzp;
-  const pm::BGrid G = pm::tw_psib<LPL>(psi, b1, b2, nz, nb, ws, psib_s);
+  const pm::BGrid G = pm::tw_psib<LPL>(psi, b1, b2, nz, nb, ws, psib_s, reinterpret_cast<int*>(psib_s + a.nbp));
   for (int i = L; i < nb; i += 32) {
     a.psib[m * nb + i] = psib_s[i];
     if (a.bgrid) a.bgrid[m * nb + i] = G.at(i);
@@ -112,11 +112,13 @@ PM_GLOBAL void k_so(SoArgs a) {
   const int nz = M.nz, ny = M.ny, L = rt::lane(), W = rt::warp_in_block(), nthr = rt::warps_per_block() * 32;
   double* zs = rt::smem();
   double* ysm = zs + a.nzp + 4;
-  double* bss = ysm + a.nyp + (size_t)(3 * a.nyp + (BVP ? 4 * a.nzp : 0)) * W;
+  double* tap = ysm + a.nyp;
+  double* bss = tap + 4 * a.nzp + (size_t)(3 * a.nyp + (BVP ? 4 * a.nzp : 0)) * W;
   double* sinv = bss + a.nyp;
   double* tau_s = sinv + a.nyp;
   for (int i = W * 32 + L; i < a.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
   for (int i = W * 32 + L; i < a.nyp; i += nthr) ysm[i] = M.y[i < ny ? i : ny - 1];
+  pm::taper_fill<LPL>(tap, M.so_sill_taper, M.so_ek_taper, M.so_top_taper, M.so_bot_taper, nz, W * 32 + L, nthr);
   rt::syncblock();
   const long long m = rt::block_idx() * rt::warps_per_block() + W;
   if (m >= M.M) return;
@@ -133,7 +135,7 @@ PM_GLOBAL void k_so(SoArgs a) {
   }
   so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
   so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
-  so.sill = M.so_sill_taper; so.ektap = M.so_ek_taper; so.toptap = M.so_top_taper; so.bottap = M.so_bot_taper;
+  so.sill = tap; so.ektap = tap + a.nzp; so.toptap = tap + 2 * a.nzp; so.bottap = tap + 3 * a.nzp;
   so.c = BVP ? vat(M.so_c, m) : 0.0;
   so.with_Ek = M.so_bvp_with_Ek;
   so.bvp_s = tau_s + a.nyp;
@@ -359,7 +361,7 @@ int pmoc_thermwind_psib(int64_t M, int32_t nz, int32_t nb, pmoc_vec Psi, pmoc_ve
   PM_DISPATCH_LPL(nz, {
     a.nzp = 32 * LPL;
     return launch(k_psib<LPL>, blocks_for(M), 32 * kWarpsPerBlock,
-                  sizeof(double) * (size_t)(6 * a.nzp + a.nbp) * kWarpsPerBlock, stream, a);
+                  sizeof(double) * (size_t)(6 * a.nzp + a.nbp + a.nbp / 2 + 2) * kWarpsPerBlock, stream, a);
   });
   return PMOC_OK;
 }
@@ -377,7 +379,8 @@ int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, do
   const bool bvp = so->so_c.ptr != nullptr;
   PM_DISPATCH_LPL(so->nz, {
     a.nzp = 32 * LPL;
-    const size_t smem = sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + (3 * a.nyp + (bvp ? 4 * a.nzp : 0)) * kWarpsPerBlock);
+    const size_t smem =
+        sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + 4 * a.nzp + (3 * a.nyp + (bvp ? 4 * a.nzp : 0)) * kWarpsPerBlock);
     if (bvp) return launch(k_so<LPL, true>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
     return launch(k_so<LPL, false>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
   });
