@@ -44,7 +44,7 @@ struct SmemPlan {
   int off_dzu, off_rdzu, off_dzc, off_rdzc;                        // per block, bit-faithful step only
   int off_tap;                                                      // per block, 4*nzp Psi_SO tapers
   int off_warp0, per_warp;                                          // per warp region
-  int w_col[2];                                                     // column tables of basin / north (4*nzp each)
+  int w_col[2];                                                     // column tables of basin / north (3 or 4 nzp each)
   int w_remap, w_psib, w_cnt, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
@@ -77,8 +77,9 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   if (flags & PMOC_HAS_SO) { s.off_tap = o; o += 4 * s.nzp; }
   s.off_warp0 = o;
   int w = 0;
-  s.w_col[0] = w; w += 4 * s.nzp;
-  if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += 4 * s.nzp; }
+  const int colw = exact ? 4 : 3;  // arrays per column table
+  s.w_col[0] = w; w += colw * s.nzp;
+  if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += colw * s.nzp; }
   if ((flags & PMOC_ISO) && !exact) {
     s.w_remap = w; w += 6 * s.nzp;
     s.w_psib = w; w += s.nbp;
@@ -112,7 +113,7 @@ PM_DEV pm::GeoTab geo_of(double* sm, const SmemPlan& sp) {
 }
 PM_DEV pm::ColTab coltab_of(double* ws, const SmemPlan& sp, int which) {
   double* t = ws + sp.w_col[which];
-  return pm::ColTab{t, t + sp.nzp, t + 2 * sp.nzp, t + 3 * sp.nzp};
+  return pm::ColTab{t, t + sp.nzp, t + 2 * sp.nzp};
 }
 PM_DEV pm::ExactGeo exactgeo_of(double* sm, const SmemPlan& sp) {
   return pm::ExactGeo{sm + sp.off_dzu, sm + sp.off_rdzu, sm + sp.off_dzc, sm + sp.off_rdzc};

@@ -69,14 +69,14 @@ PM_DEV double wscan_excl(double v) {
 // weff = wA - d(A kappa)/dz is fixed between two streamfunction updates, so p, q are rebuilt
 // only then.  Everything state-independent is tabulated once per launch:
 //   per block  (GeoTab, lane-major): 1/dzu, 1/dzd, 1/(dzc dzu), 1/(dzc dzd), z
-//   per member (ColTab, lane-major): KU = dt kappa/(dzc dzu), KD = dt kappa/(dzc dzd), RA = dt/A, dAk
+//   per member (ColTab, lane-major): dt kappa, RA = dt/A, dAk
 // Boundary and padding levels get p = q = 0.
 struct GeoTab {
   const double *zs;                      // natural order, nzp+4 (padded with z[nz-1])
   const double *zl, *rdu, *rdd, *ruu, *rdd2;  // lane-major, nzp each
 };
 struct ColTab {
-  double *ku, *kd, *ra, *dak;  // lane-major, nzp each (per warp)
+  double *kdt, *ra, *dak;  // lane-major, nzp each (per warp): dt*kappa, dt/Area, d(A kappa)/dz
 };
 
 // block-cooperative fill of the geometry tables (call before the block barrier)
@@ -117,16 +117,13 @@ PM_DEV void col_tabulate(const ColTab& T, const GeoTab& G, const double* PM_REST
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j), s = lm(j);
-    double ku = 0., kd = 0., ra = 0., dk = 0.;
+    double kdt = 0., ra = 0., dk = 0.;
     if (i >= 1 && i < nz - 1) {
-      const double kdt = dt * kappa[i];
-      ku = kdt * G.ruu[s];
-      kd = kdt * G.rdd2[s];
+      kdt = dt * kappa[i];
       ra = dt / Area[i];
       dk = dAk[i];
     }
-    T.ku[s] = ku;
-    T.kd[s] = kd;
+    T.kdt[s] = kdt;
     T.ra[s] = ra;
     T.dak[s] = dk;
   }
@@ -143,8 +140,9 @@ PM_DEV void col_coeffs(double (&p)[LPL], double (&q)[LPL], const double (&wA)[LP
     if (i >= 1 && i < nz - 1) {
       const double weff = wA[j] - T.dak[s];
       const double ra = T.ra[s];
-      pj = T.ku[s];
-      qj = T.kd[s];
+      const double kdt = T.kdt[s];
+      pj = kdt * G.ruu[s];
+      qj = kdt * G.rdd2[s];
       if (weff < 0)
         pj = pj - weff * (ra * G.rdu[s]);
       else
@@ -630,7 +628,7 @@ PM_DEV bool sgn(double v) { return std::signbit(v); }
 // scipy.optimize.brentq(lambda y: bs(y) - bval, ya, yb) with the default tolerances --
 // statement-for-statement the iteration of scipy/optimize/Zeros/brentq.c (Brent 1973), so a
 // multi-root bs(y) resolves to the root the reference finds.
-PM_DEV double outcrop_brent(double bval, const double* ygrid, const double* bs, int ny, int south, bool* sign_error) {
+PM_COLD double outcrop_brent(double bval, const double* ygrid, const double* bs, int ny, int south, bool* sign_error) {
   const double xtol = 2e-12, rtol = 8.881784197001252e-16;
   double xpre = ygrid[south], xcur = ygrid[ny - 1];
   double xblk = 0., fblk = 0., spre = 0., scur = 0.;
@@ -771,9 +769,11 @@ PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int n
 // np.mean(tau(np.linspace(y0, yN, 100))) for tau given on the y grid (psi_SO.py:239):
 // numpy's linspace (arange*step + start, last point = stop), np.interp and the pairwise
 // reduction of 100 terms (8 accumulators over 96 terms, tree combine, 4 trailing adds).
-PM_DEV double tau_mean100(double y0, double yN, const double* ygrid, const double* tau_y, int ny) {
+PM_COLD double tau_mean100(double y0, double yN, const double* ygrid, const double* tau_y, int ny) {
   const double delta = yN - y0, step = delta / 99.0;
-  auto at = [&](int p) {
+  double r[8];
+  double res = 0.0;
+  for (int p = 0; p < 100; ++p) {
     double yp;
     if (p == 99)
       yp = yN;
@@ -781,17 +781,16 @@ PM_DEV double tau_mean100(double y0, double yN, const double* ygrid, const doubl
       yp = (double)p / 99.0 * delta + y0;
     else
       yp = (double)p * step + y0;
-    return interp1(yp, ygrid, tau_y, ny);
-  };
-  double r[8];
-  PM_UNROLL
-  for (int k = 0; k < 8; ++k) r[k] = at(k);
-  for (int blk = 1; blk < 12; ++blk) {
-    PM_UNROLL
-    for (int k = 0; k < 8; ++k) r[k] = r[k] + at(blk * 8 + k);
+    const double v = interp1(yp, ygrid, tau_y, ny);
+    if (p < 8) {
+      r[p] = v;
+    } else if (p < 96) {
+      r[p & 7] = r[p & 7] + v;
+    } else {
+      if (p == 96) res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+      res = res + v;
+    }
   }
-  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
-  for (int p = 96; p < 100; ++p) res = res + at(p);
   return res / 100.0;
 }
 
@@ -974,7 +973,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
   } else {
     if (!S.mono) *status |= 2u;
     PM_UNROLL
-    for (int j = 0; j < LPL; ++j) {
+    for (int j = 0; j < LPL; ++j) {  // (registers: must stay unrolled; the heavy callee is out of line)
       const double bi = b[j];
       double yo = 0.;
       if (lev<LPL>(j) < nz) {

@@ -185,16 +185,11 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       apply(psi_tw, iso_n, psi_so);
   };
 
-  if (a.diagnose_only) {
-    refresh(true);
-    if (M.status && L == 0) M.status[m] |= status;
-    return;
-  }
-
   const long long K = M.K, it_end = a.it0 + a.nsteps;
   // carried streamfunctions -> stencils (the loop uses the previous diagnosis until it % K == 0);
   // the 'jn' order diagnoses at the top of iteration it % K == 0 and then needs nothing carried
-  if (!ML || a.it0 % K != 0) {
+  const bool dg = a.diagnose_only != 0;
+  if (!dg && (!ML || a.it0 % K != 0)) {
     double t1[LPL], t2[LPL], t3[LPL];
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) t1[j] = t2[j] = t3[j] = 0.0;
@@ -204,7 +199,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     apply(t1, t2, t3);
   }
 
-  if (!ML) {
+  if (!ML && !dg) {
     // boundary values of "plain" columns are invariant under the step: set them once
     // (surface: column.py:230-231, bottom: column.py:232)
     if (!cb.conv) pm::set_level<LPL>(cb.b, nz - 1, cb.bs);
@@ -213,10 +208,24 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       if (!cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
       if (cn.plain) col_bottom<LPL>(cn, zs);
     }
-    // last iteration of this launch that re-diagnoses: only that one writes diagnostics to HBM
-    const long long last_refresh = ((it_end - 1) / K) * K;
-    long long ii = a.it0;
-    while (ii < it_end) {
+  }
+  // One loop for both orders, with a single (inlined) copy of the diagnosis:
+  //   'post' (example_twocol_plusSO.py:99-115): step ... step(it % K == 0) -> refresh
+  //   'jn'   (run_JansenNadeau_2018.py:201-261): refresh at the top of it % K == 0 -> steps
+  // Only the last refresh of a launch writes the diagnostics to HBM.
+  const long long last_refresh = ((it_end - 1) / K) * K;
+  const bool two_var_b = M.basin.nvar > 1, two_var_n = M.north.nvar > 1;
+  long long ii = a.it0;
+  bool refresh_next = dg || (ML && ii < it_end && ii % K == 0);
+  bool wr = dg || ii == last_refresh;
+  for (;;) {
+    if (refresh_next) {
+      refresh(wr);
+      refresh_next = false;
+      if (dg) break;
+    }
+    if (ii >= it_end) break;
+    if (!ML) {
       const long long stop = ((ii + K - 1) / K) * K;  // next iteration with it % K == 0
       const bool hits = stop < it_end;
       const int n = (int)((hits ? stop + 1 : it_end) - ii);
@@ -225,15 +234,9 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         if (NORTH) col_advance<LPL>(cn, G, nz);
       }
       ii += n;
-      if (hits) refresh(stop == last_refresh);
-    }
-  } else {
-    // examples/run_JansenNadeau_2018.py:201-261 / run_single_global_basin.py:172-229
-    const long long last_refresh = ((it_end - 1) / K) * K;
-    const bool two_var_b = M.basin.nvar > 1, two_var_n = M.north.nvar > 1;
-    long long ii = a.it0;
-    while (ii < it_end) {
-      if (ii % K == 0) refresh(ii == last_refresh);
+      refresh_next = hits;
+      wr = stop == last_refresh;
+    } else {
       long long stop = (ii / K + 1) * K;
       if (stop > it_end) stop = it_end;
       for (; ii < stop; ++ii) {
@@ -268,7 +271,15 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         const bool sorted = pm::ml_bind_basin<LPL>(cb.b, nz, bb_s);
         pm::ml_step(ml, bb_s, pm_s, nz, sorted, ws + sp.w_bs, dt, &status);
       }
+      refresh_next = ii < it_end;  // here ii % K == 0
+      wr = ii == last_refresh;
     }
+  }
+  if (dg) {
+    if (M.status && L == 0) M.status[m] |= status;
+    return;
+  }
+  if (ML) {
     if (L == 0) {
       M.basin.bbot[m] = cb.bbot;
       M.north.bbot[m] = cn.bbot;
