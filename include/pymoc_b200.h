@@ -27,6 +27,7 @@ extern "C" {
 
 #define PMOC_ABI_VERSION 1
 #define PMOC_MAX_NZ_WARP 256 /* one warp per member up to this many levels */
+#define PMOC_MAX_NZ_WIDE 4096 /* one CTA per member up to this many levels ('jn' topology only) */
 #define PMOC_MAX_NY_ML 64    /* SO_ML surface points per member */
 
 typedef enum {
@@ -122,12 +123,18 @@ typedef struct {
   double *Psi_so, *Psi_Ek, *Psi_GM;       /* [M, nz] Sv */
   double* ml_Psi_s;                       /* [M, ny] Sv */
   uint32_t* status;                       /* [M] PMOC_ST_* bits, OR-ed */
+
+  /* device scratch, needed only when nz > PMOC_MAX_NZ_WARP: pmoc_model_scratch_bytes(m) bytes.
+     The library never allocates device memory itself (except in pmoc_model_run_host). */
+  void* scratch;
+  uint64_t scratch_bytes;
 } pmoc_model;
 
 /* library / device ----------------------------------------------------------------------- */
 int pmoc_abi_version(void);
 const char* pmoc_last_error(void);     /* text of the last PMOC_ECUDA on this thread */
 int pmoc_device_info(int* sm_count, int* cc_major, int* cc_minor);
+uint64_t pmoc_model_scratch_bytes(const pmoc_model* m); /* 0 when nz <= PMOC_MAX_NZ_WARP */
 
 /* Diagnose all streamfunctions of the model from its current state -- what the scripts do
  * before their loop (examples/example_twocol_plusSO.py:61-80: AMOC.solve(); AMOC.Psibz();

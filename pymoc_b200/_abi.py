@@ -36,11 +36,11 @@ class Model(C.Structure):
       ('ml_surflux', Vec), ('ml_rest_mask', Vec), ('ml_b_rest', Vec),
       ('Psi_tw', C.c_void_p), ('Psi_iso_b', C.c_void_p), ('Psi_iso_n', C.c_void_p), ('psib', C.c_void_p),
       ('bgrid', C.c_void_p), ('Psi_so', C.c_void_p), ('Psi_Ek', C.c_void_p), ('Psi_GM', C.c_void_p),
-      ('ml_Psi_s', C.c_void_p), ('status', C.c_void_p),
+      ('ml_Psi_s', C.c_void_p), ('status', C.c_void_p), ('scratch', C.c_void_p), ('scratch_bytes', C.c_uint64),
   ]
 
 
-EXPORTS = ('pmoc_abi_version', 'pmoc_last_error', 'pmoc_device_info', 'pmoc_model_diagnose', 'pmoc_model_run',
+EXPORTS = ('pmoc_abi_version', 'pmoc_last_error', 'pmoc_device_info', 'pmoc_model_scratch_bytes', 'pmoc_model_diagnose', 'pmoc_model_run',
            'pmoc_model_run_host', 'pmoc_column_timestep', 'pmoc_thermwind_solve', 'pmoc_thermwind_psib',
            'pmoc_so_solve', 'pmoc_ml_timestep', 'pmoc_fp64_peak')
 
@@ -53,6 +53,7 @@ def declare(lib):
   lib.pmoc_last_error.restype = C.c_char_p
   lib.pmoc_last_error.argtypes = []
   lib.pmoc_device_info.argtypes = [P(C.c_int), P(C.c_int), P(C.c_int)]
+  lib.pmoc_model_scratch_bytes.argtypes = [P(Model)]
   lib.pmoc_model_diagnose.argtypes = [P(Model), C.c_void_p]
   lib.pmoc_model_run.argtypes = [P(Model), C.c_int64, C.c_int64, C.c_void_p]
   lib.pmoc_model_run_host.argtypes = [P(Model), C.c_int64, C.c_int64]
@@ -66,8 +67,9 @@ def declare(lib):
   lib.pmoc_ml_timestep.argtypes = [P(Model), Vec, Vec, C.c_double, C.c_void_p, C.c_void_p]
   lib.pmoc_fp64_peak.argtypes = [P(C.c_double), P(C.c_double), C.c_void_p]
   for name in EXPORTS:
-    if name != 'pmoc_last_error':
+    if name not in ('pmoc_last_error', 'pmoc_model_scratch_bytes'):
       getattr(lib, name).restype = C.c_int
+  lib.pmoc_model_scratch_bytes.restype = C.c_uint64
   if lib.pmoc_abi_version() != ABI_VERSION:
     raise RuntimeError('pymoc_b200: ABI version mismatch (library %d, python %d)' %
                        (lib.pmoc_abi_version(), ABI_VERSION))

@@ -123,6 +123,9 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
   d.Psi_GM = mr.out(m->Psi_GM, (size_t)M * nz, carry);
   d.ml_Psi_s = mr.out(m->ml_Psi_s, (size_t)M * ny, carry);
   d.status = mr.out(m->status, (size_t)M, true);
+  d.scratch = nullptr;
+  d.scratch_bytes = pmoc_model_scratch_bytes(m);
+  if (d.scratch_bytes) d.scratch = mr.alloc((size_t)d.scratch_bytes);
   int rc = PMOC_OK;
   if (mr.err == cudaSuccess) {
     if (it0 == 0 && !(f & PMOC_ORDER_JN)) rc = pmoc_model_diagnose(&d, mr.s);

@@ -276,6 +276,7 @@ int run_model(const pmoc_model* m, long long it0, long long nsteps, int diagnose
   if (int rc = check_model(m)) return rc;
   if (nsteps < 0 || it0 < 0) return fail(PMOC_EINVAL, "negative it0 / nsteps");
   if (!diagnose_only && nsteps == 0) return PMOC_OK;
+  if (m->nz > PMOC_MAX_NZ_WARP) return pmoc_run_model_wide(m, it0, nsteps, diagnose_only, stream);
   RunArgs ra;
   ra.m = *m;
   ra.m.flags &= ~PMOC_SO_BVP;
@@ -321,6 +322,11 @@ int pmoc_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   if (cc_minor) *cc_minor = p.minor;
   return PMOC_OK;
 #endif
+}
+
+uint64_t pmoc_model_scratch_bytes(const pmoc_model* m) {
+  if (!m || m->nz <= PMOC_MAX_NZ_WARP) return 0;
+  return sizeof(double) * ((uint64_t)4 * m->nz + (uint64_t)m->M * 6 * m->nz);
 }
 
 int pmoc_model_diagnose(const pmoc_model* m, void* stream) { return run_model(m, 0, 0, 1, stream); }

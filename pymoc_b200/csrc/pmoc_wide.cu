@@ -1,0 +1,567 @@
+// Block-per-member kernels for columns too tall for one warp (256 < nz <= 4096): the 'jn'
+// topology of examples/run_single_global_basin.py / run_JansenNadeau_2018.py (two convecting
+// columns, thermal wind with isopycnal remap, explicit Psi_SO, SO_ML).
+//
+// One CTA owns one member.  k_wide_steps keeps both buoyancy profiles, the cell gradients and
+// Psi_mod in shared memory for all the steps of a launch and streams the per-level constants
+// (geometry, kappa, -weff, Area) from a caller-provided scratch buffer that stays L2 resident;
+// the arithmetic is the bit-faithful step of pm::col_step_exact, level by level.  At the stable
+// time step of such grids the streamfunctions are re-diagnosed once in tens of thousands of steps
+// (K = 72 000 at nz = 4096), so the diagnosis is a separate, plain kernel (k_wide_refresh) and the
+// host loop in run_model_wide alternates the two.  First correct version: the constants are
+// re-read every step instead of being register/shared resident.
+#include "pmoc_common.cuh"
+
+namespace pmk {
+
+constexpr int kWideThreads = 256;
+
+struct WideArgs {
+  pmoc_model m;
+  long long it0, nsteps;
+  double* geo;   // scratch: [4][nz] dzu, 1/dzu, dzc, 1/dzc (shared by all members)
+  double* memb;  // scratch: per member [6][nz]: -weff basin v0, v1, -weff north v0, v1, 1/Area basin, 1/Area north
+};
+
+PM_DEV int wtid() { return rt::warp_in_block() * 32 + rt::lane(); }
+PM_DEV int wnthr() { return rt::warps_per_block() * 32; }
+
+// ---- small block collectives on shared memory ------------------------------------------------
+// exclusive prefix (reverse = false) or exclusive suffix (reverse = true) sum of a[0..n) in place;
+// red: one double per thread.  Fixed association: chunk by chunk, left to right (right to left).
+PM_DEV void block_scan_excl(double* a, int n, double* red, bool reverse) {
+  const int T = wnthr(), t = wtid();
+  const int chunk = (n + T - 1) / T;
+  const int lo = t * chunk < n ? t * chunk : n, hi = lo + chunk < n ? lo + chunk : n;
+  double s = 0.0;
+  if (!reverse)
+    for (int i = lo; i < hi; ++i) s = s + a[i];
+  else
+    for (int i = hi - 1; i >= lo; --i) s = s + a[i];
+  red[t] = s;
+  rt::syncblock();
+  if (t == 0) {
+    double run = 0.0;
+    if (!reverse)
+      for (int k = 0; k < T; ++k) { const double v = red[k]; red[k] = run; run = run + v; }
+    else
+      for (int k = T - 1; k >= 0; --k) { const double v = red[k]; red[k] = run; run = run + v; }
+  }
+  rt::syncblock();
+  double run = red[t];
+  if (!reverse)
+    for (int i = lo; i < hi; ++i) { const double v = a[i]; a[i] = run; run = run + v; }
+  else
+    for (int i = hi - 1; i >= lo; --i) { const double v = a[i]; a[i] = run; run = run + v; }
+  rt::syncblock();
+}
+
+// block-wide OR of a predicate / max of an int, through two shared ints
+PM_DEV bool block_any(bool p, int* flag) {
+  if (wtid() == 0) *flag = 0;
+  rt::syncblock();
+  if (rt::ballot(p) != 0 && rt::lane() == 0) rt::atomic_add_shared(flag, 1);
+  rt::syncblock();
+  const bool r = *flag != 0;
+  rt::syncblock();
+  return r;
+}
+PM_DEV int block_max(int v, int* slot) {
+  if (wtid() == 0) *slot = -0x7fffffff;
+  rt::syncblock();
+  const int w = rt::max_i(v);
+  if (rt::lane() == 0) rt::atomic_max_shared(slot, w);
+  rt::syncblock();
+  const int r = *slot;
+  rt::syncblock();
+  return r;
+}
+PM_DEV int block_min(int v, int* slot) { return -block_max(-v, slot); }
+PM_DEV unsigned block_or(unsigned v, int* slot) {
+  if (wtid() == 0) *slot = 0;
+  rt::syncblock();
+  for (unsigned bit = 1; bit <= 64u; bit <<= 1)
+    if (rt::ballot((v & bit) != 0) != 0 && rt::lane() == 0) rt::atomic_or_shared(slot, (int)bit);
+  rt::syncblock();
+  const unsigned r = (unsigned)*slot;
+  rt::syncblock();
+  return r;
+}
+
+// ---- geometry -----------------------------------------------------------------------------------
+PM_GLOBAL void k_wide_geo(WideArgs a) {
+  const int nz = a.m.nz;
+  const double* z = a.m.z;
+  for (long long i = rt::block_idx() * wnthr() + wtid(); i < nz; i += (long long)wnthr() * 64) {
+    double du = 1., dc = 1.;
+    if (i < nz - 1) du = z[i + 1] - z[i];
+    if (i >= 1 && i < nz - 1) dc = 0.5 * ((z[i + 1] - z[i]) + (z[i] - z[i - 1]));
+    a.geo[i] = du;
+    a.geo[nz + i] = 1. / du;
+    a.geo[2 * nz + i] = dc;
+    a.geo[3 * nz + i] = 1. / dc;
+  }
+}
+
+// ---- diagnosis of the streamfunctions -----------------------------------------------------------
+// Psi_Thermwind.solve + Psibz + Psi_SO.solve for one member per CTA, results to global memory
+// (same expressions as pm::tw_solve / tw_psib / interp_bgrid / so_solve, level loops instead of
+// register chunks).
+PM_GLOBAL void k_wide_refresh(WideArgs a) {
+  const pmoc_model& M = a.m;
+  const int nz = M.nz, ny = M.ny, nb = M.nb, T = wnthr(), t = wtid();
+  const long long m = rt::block_idx();
+  double* sm = rt::smem();
+  // six level arrays: the two profiles and four work arrays
+  double *b1 = sm, *b2 = sm + nz, *A = sm + 2 * nz, *B = sm + 3 * nz, *C = sm + 4 * nz, *P = sm + 5 * nz;
+  double* psib_s = sm + 6 * nz;
+  const int nbp = (nb + 3) & ~3, nyp = (ny + 3) & ~3;
+  int* cnt = reinterpret_cast<int*>(psib_s + nbp);
+  double* red = psib_s + nbp + nbp / 2 + 2;
+  double* bs_s = red + 64 + T;
+  double* sinv = bs_s + nyp;
+  double* ysm = sinv + nyp;
+  int* ibox = reinterpret_cast<int*>(ysm + nyp);  // 4 ints of broadcast space
+  const double* z = M.z;
+  unsigned status = 0;
+
+  for (int i = t; i < nz; i += T) {
+    b1[i] = M.basin.b[m * nz + i];
+    b2[i] = M.north.b[m * nz + i];
+  }
+  for (int i = t; i < nyp; i += T) {
+    ysm[i] = M.y[i < ny ? i : ny - 1];
+    bs_s[i] = M.ml_bs[m * ny + (i < ny ? i : ny - 1)];
+  }
+  rt::syncblock();
+
+  // --- thermal wind: Psi'' = (b2-b1)/f (psi_thermwind.py:123-135), see pm::tw_solve.  A = T (Simpson
+  // increments of Psi'), B = their exclusive prefix, C = cell integrals -> exclusive prefix, P = Psi (Sv)
+  const double rf = 1. / vat(M.tw_f, m);
+  for (int i = t; i < nz; i += T) {
+    double tt = 0.0;
+    if (i < nz - 1) {
+      const double gi = rf * (b2[i] - b1[i]), gi1 = rf * (b2[i + 1] - b1[i + 1]);
+      const double h = z[i + 1] - z[i], gm = 0.5 * (gi + gi1);
+      tt = h / 6. * (gi + 4. * gm + gi1);
+    }
+    A[i] = tt;
+    B[i] = tt;
+  }
+  rt::syncblock();
+  block_scan_excl(B, nz, red + 64, false);
+  for (int i = t; i < nz; i += T) {
+    double cell = 0.0;
+    if (i < nz - 1) {
+      const double gi = rf * (b2[i] - b1[i]), gi1 = rf * (b2[i + 1] - b1[i + 1]);
+      const double h = z[i + 1] - z[i];
+      cell = h * B[i] + h * A[i] / 2. - h * h / 12. * (gi1 - gi);
+    }
+    C[i] = cell;
+  }
+  rt::syncblock();
+  block_scan_excl(C, nz, red + 64, false);
+  {
+    const double total = C[nz - 1], z0 = z[0], H = z[nz - 1] - z[0];
+    for (int i = t; i < nz; i += T) {
+      const double v = pm::div_const(C[i] - total * ((z[i] - z0) / H), pm::kSv, 1.0 / pm::kSv);
+      P[i] = v;
+      M.Psi_tw[m * nz + i] = v;
+    }
+  }
+  rt::syncblock();
+
+  // --- isopycnal remap (psi_thermwind.py:170-208), see pm::tw_psib
+  double lo = INFINITY, hi = -INFINITY;
+  bool unsorted = false;
+  for (int i = t; i < nz; i += T) {
+    lo = b1[i] < lo ? b1[i] : lo;
+    lo = b2[i] < lo ? b2[i] : lo;
+    hi = b1[i] > hi ? b1[i] : hi;
+    hi = b2[i] > hi ? b2[i] : hi;
+    if (i < nz - 1) {
+      const double u = -(P[i + 1] - P[i]);
+      unsorted |= !(b1[i + 1] >= b1[i]) || !(b2[i + 1] >= b2[i]) || u != u;
+    }
+  }
+  lo = rt::wmin(lo);
+  hi = rt::wmax(hi);
+  if (rt::lane() == 0) {
+    red[rt::warp_in_block()] = lo;
+    red[32 + rt::warp_in_block()] = hi;
+  }
+  rt::syncblock();
+  for (int w = 0; w < rt::warps_per_block(); ++w) {
+    const double l = red[w], h2 = red[32 + w];
+    lo = (l < lo || lo != lo) ? l : lo;
+    hi = (h2 > hi || hi != hi) ? h2 : hi;
+  }
+  rt::syncblock();
+  pm::BGrid G;
+  G.lo = lo;
+  G.hi = hi;
+  G.nb = nb;
+  G.step = (hi - lo) / (double)(nb - 1);
+  const bool direct = block_any(unsorted, ibox);
+  // transport of cell c and the column it is taken from
+  auto cell_u = [&](int c) { return -(P[c + 1] - P[c]); };
+  if (!direct) {
+    // A = S_1, B = S_2: S_X[k] = sum_{c >= k} [cell c uses X] u_c  (exclusive suffix + own)
+    for (int i = t; i < nz; i += T) {
+      const double u = i < nz - 1 ? cell_u(i) : 0.0;
+      A[i] = u < 0 ? 0.0 : u;
+      B[i] = u < 0 ? u : 0.0;
+    }
+    rt::syncblock();
+    block_scan_excl(A, nz, red + 64, true);
+    block_scan_excl(B, nz, red + 64, true);
+    for (int i = t; i < nz; i += T) {
+      const double u = i < nz - 1 ? cell_u(i) : 0.0;
+      A[i] = A[i] + (u < 0 ? 0.0 : u);
+      B[i] = B[i] + (u < 0 ? u : 0.0);
+    }
+    for (int i = t; i <= nb; i += T) cnt[i] = 0;
+    rt::syncblock();
+    for (int i = t; i < nz; i += T) {
+      rt::atomic_add_shared(&cnt[pm::bgrid_count_le(G, b1[i])], 1);
+      rt::atomic_add_shared(&cnt[pm::bgrid_count_le(G, b2[i])], 1 << 16);
+    }
+    rt::syncblock();
+    if (t == 0) {  // inclusive prefix over the classes (nb is a few hundred)
+      int run = 0;
+      for (int i = 0; i <= nb; ++i) {
+        run += cnt[i];
+        cnt[i] = run;
+      }
+    }
+    rt::syncblock();
+    for (int i = t; i < nb; i += T) {
+      const double x = G.at(i);
+      const int k1 = cnt[i] & 0xffff, k2 = cnt[i] >> 16;  // #{levels with bX < x}
+      double c1 = 0.0, c2 = 0.0;
+      if (k1 < nz) {
+        const double bk = b1[k1];
+        c1 = A[k1];
+        if (k1 > 0 && bk != x) {
+          const double u = cell_u(k1 - 1);
+          c1 = c1 + (bk - x) * (u < 0 ? 0.0 : u / (bk - b1[k1 - 1]));
+        }
+        if (bk == x)  // flat cells taken from column 1 sitting exactly on the class: 0/0 in the reference
+          for (int c = k1; c + 1 < nz && b1[c + 1] == x; ++c)
+            if (!(cell_u(c) < 0)) c1 = NAN;
+      }
+      if (k2 < nz) {
+        const double bk = b2[k2];
+        c2 = B[k2];
+        if (k2 > 0 && bk != x) {
+          const double u = cell_u(k2 - 1);
+          c2 = c2 + (bk - x) * (u < 0 ? u / (bk - b2[k2 - 1]) : 0.0);
+        }
+        if (bk == x)
+          for (int c = k2; c + 1 < nz && b2[c + 1] == x; ++c)
+            if (cell_u(c) < 0) c2 = NAN;
+      }
+      psib_s[i] = c1 + c2;
+    }
+  } else {
+    // direct path: every class against every cell (inverted cells / NaN)
+    for (int i = t; i < nb; i += T) {
+      const double bg = G.at(i);
+      double acc = 0.0;
+      for (int c = 0; c < nz - 1; ++c) {
+        const double u = cell_u(c);
+        const bool from2 = u < 0;
+        const double bot = from2 ? b2[c] : b1[c], top = from2 ? b2[c + 1] : b1[c + 1];
+        double f = (top - bg) * (1.0 / (top - bot));
+        f = f < 0. ? 0. : f;
+        f = f > 1. ? 1. : f;
+        acc = rt::fma(f, u, acc);
+      }
+      psib_s[i] = acc;
+    }
+  }
+  rt::syncblock();
+  for (int i = t; i < nb; i += T) {
+    if (M.psib) M.psib[m * nb + i] = psib_s[i];
+    if (M.bgrid) M.bgrid[m * nb + i] = G.at(i);
+  }
+  for (int i = t; i < nz; i += T) {
+    M.Psi_iso_b[m * nz + i] = pm::interp_bgrid(b1[i], G, psib_s);
+    M.Psi_iso_n[m * nz + i] = pm::interp_bgrid(b2[i], G, psib_s);
+  }
+
+  // --- Psi_SO.solve, explicit GM branch (psi_SO.py:106-140, 218-243, 302-354), see pm::so_solve
+  const pm::SoSurf S = pm::so_scan(ysm, bs_s, sinv, ny);  // every warp redundantly, same values
+  rt::syncblock();
+  if (!S.mono) status |= PMOC_ST_BS_NONMONOTONE;
+  const double tau_ave = pm::mean100(vat(M.so_tau, m));
+  const double sf = vat(M.so_f, m), srho = vat(M.so_rho, m), sL = vat(M.so_L, m), sK = vat(M.so_KGM, m),
+               smax = vat(M.so_smax, m);
+  const double pre = tau_ave / sf / srho * sL, c6 = 1e6, r6 = 1.0 / 1e6;
+  for (int i = t; i < nz; i += T) {
+    const double bi = b1[i];
+    double yo;
+    if (bi < S.mn)
+      yo = S.y0 - 1e3;
+    else if (bi > S.bsN)
+      yo = S.yN;
+    else if (S.mono && S.south < ny - 1)
+      yo = pm::outcrop_monotone(bi, ysm, bs_s, sinv, ny, S.south);
+    else {
+      bool bad = false;
+      yo = pm::outcrop_brent(bi, ysm, bs_s, ny, S.south, &bad);
+      if (bad) status |= PMOC_ST_BRENT_SIGN;
+    }
+    const double e = pm::div_const(pre * M.so_sill_taper[i] * M.so_ek_taper[i], c6, r6);
+    double dy = S.yN - yo;
+    dy = 0.1 > dy ? 0.1 : dy;
+    const double sl = z[i] / dy, ms = -smax;
+    const double mx = (sl >= ms || sl != sl) ? sl : ms;
+    double g = sK * mx * sL * M.so_top_taper[i] * M.so_bot_taper[i];
+    if (dy > S.yN - S.y0) {
+      const double alt = -e * 1e6;
+      g = (g >= alt || g != g) ? g : alt;
+    }
+    g = pm::div_const(g, c6, r6);
+    M.Psi_so[m * nz + i] = i == 0 ? 0. : e + g;
+    if (M.Psi_Ek) M.Psi_Ek[m * nz + i] = e;
+    if (M.Psi_GM) M.Psi_GM[m * nz + i] = g;
+  }
+  const unsigned all = block_or(status, ibox);
+  if (t == 0 && M.status) M.status[m] |= all;
+}
+
+// ---- the steps ----------------------------------------------------------------------------------
+PM_GLOBAL void k_wide_steps(WideArgs a) {
+  const pmoc_model& M = a.m;
+  const int nz = M.nz, ny = M.ny, T = wnthr(), t = wtid(), W = rt::warp_in_block();
+  const long long m = rt::block_idx();
+  const double dt = M.dt;
+  double* sm = rt::smem();
+  double *bb = sm, *bn = sm + nz, *gzb = sm + 2 * nz, *gzn = sm + 3 * nz, *pm_s = sm + 4 * nz;
+  const int nyp = (ny + 3) & ~3;
+  double* bs_s = sm + 5 * nz;
+  double* scan_s = bs_s + nyp;
+  double* ysm = scan_s + 320;
+  double* dbox = ysm + nyp;                          // 8 doubles of broadcast space
+  int* ibox = reinterpret_cast<int*>(dbox + 8);      // 8 ints
+  const double* z = M.z;
+  const double *dzu = a.geo, *rdzu = a.geo + nz, *dzc = a.geo + 2 * nz, *rdzc = a.geo + 3 * nz;
+  double* mem = a.memb + (size_t)m * 6 * nz;
+  double *nwb0 = mem, *nwb1 = mem + nz, *nwn0 = mem + 2 * nz, *nwn1 = mem + 3 * nz, *rab = mem + 4 * nz,
+         *ran = mem + 5 * nz;
+  const double* kapb = vrow(M.basin.kappa, m);
+  const double* kapn = vrow(M.north.kappa, m);
+  const double* dakb = vrow(M.basin.dAk, m);
+  const double* dakn = vrow(M.north.dAk, m);
+  const double* Ab = vrow(M.basin.Area, m);
+  const double* An = vrow(M.north.Area, m);
+  const int nvb = M.basin.nvar > 1 ? nz : 0, nvn = M.north.nvar > 1 ? nz : 0;  // offset of variant 1
+  unsigned status = 0;
+
+  // state and what the carried streamfunctions imply (run_JansenNadeau_2018.py:228-231)
+  int fnz = 0x7fffffff, fpos = 0x7fffffff;
+  for (int i = t; i < nz; i += T) {
+    bb[i] = M.basin.b[m * nz + i];
+    bn[i] = M.north.b[m * nz + i];
+    const double pso = M.Psi_so[m * nz + i], ib = M.Psi_iso_b[m * nz + i], in_ = M.Psi_iso_n[m * nz + i];
+    pm_s[i] = pso;
+    if (pso != 0.0 && i < fnz) fnz = i;
+    if (pso > 0.0 && i < fpos) fpos = i;
+    const bool in = i >= 1 && i < nz - 1;
+    const double wAb = (ib - pso) * 1e6, wAn = -in_ * 1e6;
+    nwb0[i] = in ? -(wAb - dakb[i]) : 0.0;
+    nwb1[i] = in ? -(wAb - dakb[nvb + i]) : 0.0;
+    nwn0[i] = in ? -(wAn - dakn[i]) : 0.0;
+    nwn1[i] = in ? -(wAn - dakn[nvn + i]) : 0.0;
+    rab[i] = 1.0 / (in ? Ab[i] : 1.0);
+    ran[i] = 1.0 / (in ? An[i] : 1.0);
+  }
+  for (int i = t; i < nyp; i += T) ysm[i] = M.y[i < ny ? i : ny - 1];
+  fnz = block_min(fnz, ibox);
+  fpos = block_min(fpos, ibox);
+  const double psi_so1 = M.Psi_so[m * nz + 1], res_b1 = M.Psi_iso_b[m * nz + 1], res_n1 = M.Psi_iso_n[m * nz + 1];
+  if (fnz == 0x7fffffff) status |= PMOC_ST_ML_INDEX;
+  const double held = pm_s[fnz == 0x7fffffff ? 0 : fnz];
+  rt::syncblock();
+  for (int i = t; i < nz && i < fnz; i += T) pm_s[i] = held;
+  rt::syncblock();
+
+  pm::MlState ml{};
+  if (W == 0) {
+    pm::ml_setup(ml, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m), vrow(M.ml_surflux, m),
+                 vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), dt, scan_s);
+    ml.first_pos = fpos == 0x7fffffff ? -1 : fpos;
+    PM_UNROLL
+    for (int e = 0; e < pm::kMLP; ++e) ml.bs[e] = M.ml_bs[m * ny + (pm::mlk(e) < ny ? pm::mlk(e) : ny - 1)];
+    if (t == 0) dbox[4] = ml.bs[0];
+  }
+  double bbot_b = M.basin.bbot[m], bbot_n = M.north.bbot[m];
+  int var_b = (M.basin.var && M.basin.nvar > 1) ? M.basin.var[m] : 0;
+  int var_n = (M.north.var && M.north.nvar > 1) ? M.north.var[m] : 0;
+  const double bs_b = vat(M.basin.bs, m), bs_n = vat(M.north.bs, m);
+  const double n2_b = vat(M.basin.N2min, m), n2_n = vat(M.north.N2min, m);
+  rt::syncblock();
+
+  for (long long it = 0; it < a.nsteps; ++it) {
+    // bottom boundary condition and bottom-boundary-layer kappa (run_JansenNadeau_2018.py:233-254)
+    {
+      const double bb0 = bb[0], bb1 = bb[1], nb0 = bn[0], nb1 = bn[1], bs0 = dbox[4];
+      if (psi_so1 < 0) { bbot_b = bs0; var_b = 1; }
+      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; var_b = 1; }
+      else if (psi_so1 >= 0) { bbot_b = bb1; var_b = 0; }
+      if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; var_n = 1; }
+      else { bbot_n = nb1; var_n = 0; }
+      if (M.basin.nvar < 2) var_b = 0;
+      if (M.north.nvar < 2) var_n = 0;
+    }
+    // convective adjustment of both columns (column.py:264-271)
+    int topb = -1, topn = -1;
+    bool anyb = false, anyn = false;
+    for (int i = t; i < nz; i += T) {
+      if (bb[i] > bs_b) anyb = true; else topb = i;
+      if (bn[i] > bs_n) anyn = true; else topn = i;
+    }
+    rt::syncblock();  // everyone has read bb[0..1] / bn[0..1] for the switches
+    if (t == 0) { ibox[0] = 0; ibox[1] = 0; ibox[2] = -1; ibox[3] = -1; }
+    rt::syncblock();
+    {
+      const unsigned mb = rt::ballot(anyb), mn = rt::ballot(anyn);
+      const int wb = rt::max_i(topb), wn = rt::max_i(topn);
+      if (rt::lane() == 0) {
+        if (mb) rt::atomic_add_shared(&ibox[0], 1);
+        if (mn) rt::atomic_add_shared(&ibox[1], 1);
+        rt::atomic_max_shared(&ibox[2], wb);
+        rt::atomic_max_shared(&ibox[3], wn);
+      }
+    }
+    rt::syncblock();
+    {
+      const bool cvb = ibox[0] != 0, cvn = ibox[1] != 0;
+      const double zcb = z[ibox[2] >= 0 ? ibox[2] : 0], zcn = z[ibox[3] >= 0 ? ibox[3] : 0];
+      for (int i = t; i < nz; i += T) {
+        if (cvb) { if (bb[i] > bs_b) bb[i] = bs_b + n2_b * (z[i] - zcb); }
+        else if (i == nz - 1) bb[i] = bs_b;
+        if (cvn) { if (bn[i] > bs_n) bn[i] = bs_n + n2_n * (z[i] - zcn); }
+        else if (i == nz - 1) bn[i] = bs_n;
+      }
+      if (t == 0) {  // column.py:232
+        bb[0] = bbot_b;
+        bn[0] = bbot_n;
+      }
+    }
+    rt::syncblock();
+    // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact
+    for (int i = t; i < nz - 1; i += T) {
+      gzb[i] = pm::div_const(bb[i + 1] - bb[i], dzu[i], rdzu[i]);
+      gzn[i] = pm::div_const(bn[i + 1] - bn[i], dzu[i], rdzu[i]);
+    }
+    rt::syncblock();
+    {
+      const double* nwb = var_b ? nwb1 : nwb0;
+      const double* nwn = var_n ? nwn1 : nwn0;
+      const double* kb = kapb + (var_b ? nvb : 0);
+      const double* kn = kapn + (var_n ? nvn : 0);
+      bool bad = false;
+      for (int i = t; i < nz; i += T) {
+        if (i >= 1 && i < nz - 1) {
+          {
+            const double up = gzb[i], dn = gzb[i - 1];
+            const double bzz = pm::div_const(up - dn, dzc[i], rdzc[i]);
+            const double nw = nwb[i], sel = nw > 0 ? up : dn;
+            const double adv = pm::div_const(nw * sel, Ab[i], rab[i]);
+            bb[i] = bb[i] + dt * (adv + kb[i] * bzz);
+          }
+          {
+            const double up = gzn[i], dn = gzn[i - 1];
+            const double bzz = pm::div_const(up - dn, dzc[i], rdzc[i]);
+            const double nw = nwn[i], sel = nw > 0 ? up : dn;
+            const double adv = pm::div_const(nw * sel, An[i], ran[i]);
+            bn[i] = bn[i] + dt * (adv + kn[i] * bzz);
+          }
+        }
+      }
+      rt::syncblock();
+      for (int i = t; i < nz - 1; i += T) bad |= !(bb[i + 1] >= bb[i]);
+      const bool sorted = !block_any(bad, ibox);
+      if (W == 0) {
+        pm::ml_step(ml, bb, pm_s, nz, sorted, bs_s, dt, &status);
+        if (t == 0) dbox[4] = ml.bs[0];
+      }
+      rt::syncblock();
+    }
+  }
+
+  for (int i = t; i < nz; i += T) {
+    M.basin.b[m * nz + i] = bb[i];
+    M.north.b[m * nz + i] = bn[i];
+  }
+  bool nan = false;
+  for (int i = t; i < nz; i += T) nan |= !(fabs(bb[i]) <= 1.79e308) || !(fabs(bn[i]) <= 1.79e308);
+  if (W == 0) {
+    PM_UNROLL
+    for (int e = 0; e < pm::kMLP; ++e) {
+      const int k = pm::mlk(e);
+      if (k < ny) {
+        M.ml_bs[m * ny + k] = ml.bs[e];
+        if (M.ml_Psi_s) M.ml_Psi_s[m * ny + k] = ml.ps[e];
+        nan |= !(fabs(ml.bs[e]) <= 1.79e308);
+      }
+    }
+  }
+  if (block_any(nan, ibox)) status |= PMOC_ST_NAN;
+  if (t == 0) {
+    M.basin.bbot[m] = bbot_b;
+    M.north.bbot[m] = bbot_n;
+    if (M.basin.var) M.basin.var[m] = var_b;
+    if (M.north.var) M.north.var[m] = var_n;
+  }
+  const unsigned all = block_or(status, ibox);  // warp 0 carries the mixed layer's bits
+  if (t == 0 && M.status) M.status[m] |= all;
+}
+
+size_t wide_refresh_smem(int nz, int ny, int nb) {
+  const int nbp = (nb + 3) & ~3, nyp = (ny + 3) & ~3;
+  return sizeof(double) * (size_t)(6 * nz + nbp + nbp / 2 + 2 + 64 + kWideThreads + 3 * nyp + 4);
+}
+size_t wide_steps_smem(int nz, int ny) {
+  const int nyp = (ny + 3) & ~3;
+  return sizeof(double) * (size_t)(5 * nz + 2 * nyp + 320 + 8 + 4);
+}
+
+}  // namespace pmk
+
+// Host loop: alternate the diagnosis (top of every iteration with it % K == 0) and step launches.
+int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, int diagnose_only, void* stream) {
+  const unsigned need = PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_ORDER_JN;
+  if ((m->flags & need) != need || (m->flags & PMOC_SO_BVP) || m->so_c.ptr || m->so_tau_on_y)
+    return fail(PMOC_EUNSUPPORTED, "nz > 256: only the 'jn' topology (two columns + thermal wind + explicit Psi_SO + SO_ML) "
+                                   "has a block-per-member kernel");
+  if (m->nz > PMOC_MAX_NZ_WIDE) return fail(PMOC_EUNSUPPORTED, "nz > 4096");
+  if (!m->scratch || m->scratch_bytes < pmoc_model_scratch_bytes(m))
+    return fail(PMOC_EINVAL, "nz > 256 needs pmoc_model.scratch of pmoc_model_scratch_bytes() bytes");
+  if (!m->Psi_tw || !m->Psi_iso_b || !m->Psi_iso_n || !m->Psi_so) return fail(PMOC_EINVAL, "diagnostic buffers missing");
+  WideArgs a;
+  a.m = *m;
+  a.geo = static_cast<double*>(m->scratch);
+  a.memb = a.geo + 4 * (size_t)m->nz;
+  a.it0 = it0;
+  a.nsteps = 0;
+  const long long K = m->K, it_end = it0 + nsteps;
+  const size_t sm_r = wide_refresh_smem(m->nz, m->ny, m->nb), sm_s = wide_steps_smem(m->nz, m->ny);
+  if (sm_r > 227 * 1024 || sm_s > 227 * 1024) return fail(PMOC_EUNSUPPORTED, "nz too large for shared memory");
+  if (int rc = launch(k_wide_geo, 64, kWideThreads, 0, stream, a)) return rc;
+  if (diagnose_only) return launch(k_wide_refresh, m->M, kWideThreads, sm_r, stream, a);
+  long long ii = it0;
+  while (ii < it_end) {
+    if (ii % K == 0)
+      if (int rc = launch(k_wide_refresh, m->M, kWideThreads, sm_r, stream, a)) return rc;
+    long long stop = (ii / K + 1) * K;
+    if (stop > it_end) stop = it_end;
+    a.it0 = ii;
+    a.nsteps = stop - ii;
+    if (int rc = launch(k_wide_steps, m->M, kWideThreads, sm_s, stream, a)) return rc;
+    ii = stop;
+  }
+  return PMOC_OK;
+}

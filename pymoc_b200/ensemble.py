@@ -182,6 +182,10 @@ class Ensemble:
         setattr(m, attr, self._vec(getattr(ml, k)))
       m.ml_Psi_s = self._out((M, ml.y.size), 'Psi_s')
     m.status = self._out((M,), 'status', np.uint32)
+    need = int(self.lib.pmoc_model_scratch_bytes(ctypes.byref(m)))
+    if need:  # columns taller than one warp handles: per-level constants live in device scratch
+      m.scratch = self._out(((need + 7) // 8,), 'scratch')
+      m.scratch_bytes = need
     return m
 
   # ------------------------------------------------------------------------------ running

@@ -367,3 +367,10 @@ if __name__ == '__main__':
     coupled_fixture('c4_literal.npz', configs.c4_jansen_nadeau(1), [0], [1, 120, 1200])
   if want('c5'):
     coupled_fixture('c5.npz', configs.c5_single_global_basin(1), [0], [1, 24, 25, 480])
+  # columns taller than one warp holds (block-per-member kernels): nz=320 over two refreshes, and the
+  # BASELINE size nz=4096 at its stable dt (K=72 000 there, so the fixture only sees the first diagnosis)
+  if want('c5_wide'):
+    coupled_fixture('c5_wide.npz', configs.c5_single_global_basin(4, nz=320, dt_days=1., axes=(2, 2, 1, 1)), [0, 3],
+                    [1, 720, 721, 1000])
+  if want('c5_4096'):
+    coupled_fixture('c5_4096.npz', configs.c5_single_global_basin(1, nz=4096, dt_days=0.01), [0], [1, 40])
