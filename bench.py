@@ -44,6 +44,9 @@ WORKLOADS = {
     'twocol': (lambda M: configs.twocol(M), 32768, 2400),
     'C3': (lambda M: configs.c3_twocol_so(M), 32768, 2400),
     'C4': (lambda M: configs.c4_jansen_nadeau(M), 32768, 2400),
+    'C5': (lambda M: configs.c5_single_global_basin(M), 32768, 2400),
+    # BASELINE configs[4]: nz=4096 (block-per-member kernels), stable dt = 0.01 d, K = 72 000
+    'C5_4096': (lambda M: configs.c5_single_global_basin(M, nz=4096, dt_days=0.01, kapfac_max=1.), 16384, 720),
 }
 
 

@@ -213,19 +213,20 @@ def c4_jansen_nadeau(M=1, axes=None):
       order='jn', iso=True)
 
 
-def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None):
+def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None, kapfac_max=2.):
   """examples/run_single_global_basin.py:40-229 with ``z=linspace(-4500,0,nz)``.
 
   Lattice: tau x kapfac x KGM x Ks (Ks <= 900: above ~1000 the
   reference itself ends in NaN / a brentq ValueError for a quarter of the lattice).  The explicit diffusion
-  needs dt <= dz^2/(2 kappa_max): 30 d at nz=46, 5 d at nz=200, 0.01 d at nz=4096 (H6).
+  needs dt <= dz^2/(2 kappa_max): 30 d at nz=46, 5 d at nz=200, 0.01 d at nz=4096 (H6) -- the
+  latter only for kapfac <= 1.08, hence ``kapfac_max`` (the nz=4096 lattice sweeps 0.5..1).
   """
   if M == 1:
     sweep = lattice(tau=[0.12], kapfac=[1.0], KGM=[1.0e3], Ks=[1.0e3])
   else:
     n = axes if axes is not None else _sizes(M, 4)
     sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
-                    kapfac=np.geomspace(0.5, 2., n[1]) if n[1] > 1 else [1.0],
+                    kapfac=np.geomspace(0.5, kapfac_max, n[1]) if n[1] > 1 else [1.0],
                     KGM=np.linspace(500., 1500., n[2]) if n[2] > 1 else [1.0e3],
                     Ks=np.linspace(500., 900., n[3]) if n[3] > 1 else [1.0e3])
   assert sweep['tau'].size == M

@@ -32,6 +32,14 @@ PM_DEV double div_const(double x, double c, double rc) {
   return rt::fma(rt::fma(-c, q, x), rc, q);
 }
 
+// a / b, IEEE.  The compiler's inline divide leaves a zero (or denormal) numerator to a ~60-instruction
+// out-of-line routine; zeros are structural here (Psi = 0 at the boundaries, z[-1] = 0, the lowest
+// class of the remap), so they are answered directly: 0 / b = +-0 for any finite non-zero b.
+PM_DEV double qdiv(double a, double b) {
+  if (a == 0.0 && b != 0.0 && fabs(b) < INFINITY) return (std::signbit(a) != std::signbit(b)) ? -0.0 : 0.0;
+  return a / b;
+}
+
 // registers <- natural-order global/shared array
 template <int LPL>
 PM_DEV void load_lev(double (&v)[LPL], const double* PM_RESTRICT g, int n, double pad) {
@@ -354,17 +362,17 @@ PM_DEV void tw_solve(double (&psi)[LPL], const double (&b1)[LPL], const double (
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) part[j] = base2 + part[j];
   const double total = get_level<LPL>(part, nz - 1);
-  const double z0 = zs[0], H = zs[nz - 1] - zs[0];
+  const double z0 = zs[0], H = zs[nz - 1] - zs[0], rH = 1.0 / H;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
-    psi[j] = i < nz ? div_const(part[j] - total * ((zs[i] - z0) / H), kSv, 1.0 / kSv) : 0.0;
+    psi[j] = i < nz ? div_const(part[j] - total * div_const(zs[i] - z0, H, rH), kSv, 1.0 / kSv) : 0.0;
   }
 }
 
 // np.linspace(bmin, bmax, nb)[i]  (numpy: arange(nb)*step + start, last element = stop)
 struct BGrid {
-  double lo, hi, step;
+  double lo, hi, step, rstep;  // rstep = 1/step (for div_const)
   int nb;
   PM_DEV double at(int i) const { return i == nb - 1 ? hi : (double)i * step + lo; }
 };
@@ -376,7 +384,7 @@ PM_DEV int bgrid_count_le(const BGrid& G, double v) {
   if (v < G.lo) return 0;
   if (v >= G.hi) return nb;
   if (!(G.step > 0.)) return v >= G.lo ? nb : 0;
-  const double r = (v - G.lo) / G.step;
+  const double r = div_const(v - G.lo, G.step, G.rstep);
   int p = r < (double)(nb - 1) ? (int)r + 1 : nb;
   while (p < nb && G.at(p) <= v) ++p;
   while (p > 0 && G.at(p - 1) > v) --p;
@@ -434,6 +442,7 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
   G.hi = rt::wmax(hi);
   G.nb = nb;
   G.step = (G.hi - G.lo) / (double)(nb - 1);
+  G.rstep = 1.0 / G.step;
   if (rt::ballot(unsorted) == 0) {
     double *b1_s = rs, *b2_s = rs + nzp, *w1_s = rs + 2 * nzp, *w2_s = rs + 3 * nzp, *S1_s = rs + 4 * nzp,
            *S2_s = rs + 5 * nzp;
@@ -572,7 +581,7 @@ PM_DEV double interp_bgrid(double x, const BGrid& G, const double* psib_s) {
   if (x < G.lo) return psib_s[0];
   int j = nb - 1;
   if (G.step > 0.) {
-    const double r = (x - G.lo) / G.step;
+    const double r = div_const(x - G.lo, G.step, G.rstep);
     j = r < (double)(nb - 1) ? (int)r : nb - 1;
     while (j < nb - 1 && G.at(j + 1) <= x) ++j;
     while (j > 0 && G.at(j) > x) --j;
@@ -582,7 +591,7 @@ PM_DEV double interp_bgrid(double x, const BGrid& G, const double* psib_s) {
   const double fj = psib_s[j];
   if (xj == x) return fj;
   const double xj1 = G.at(j + 1), fj1 = psib_s[j + 1];
-  const double slope = (fj1 - fj) / (xj1 - xj);
+  const double slope = qdiv(fj1 - fj, xj1 - xj);
   double res = slope * (x - xj) + fj;
   if (res != res) {
     res = slope * (x - xj1) + fj1;
@@ -1006,9 +1015,9 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     const double z = zs[i < nz ? i : nz - 1];
     double g;
     if (BVP) {
-      g = P.KGM * z / dy * P.L * P.toptap[s] * P.bottap[s];
+      g = qdiv(P.KGM * z, dy) * P.L * P.toptap[s] * P.bottap[s];
     } else {
-      const double sl = z / dy, ms = -P.smax;
+      const double sl = qdiv(z, dy), ms = -P.smax;
       const double mx = (sl >= ms || sl != sl) ? sl : ms;
       g = P.KGM * mx * P.L * P.toptap[s] * P.bottap[s];
     }

@@ -202,6 +202,7 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
   G.hi = hi;
   G.nb = nb;
   G.step = (hi - lo) / (double)(nb - 1);
+  G.rstep = 1.0 / G.step;
   const bool direct = block_any(unsorted, ibox);
   // transport of cell c and the column it is taken from
   auto cell_u = [&](int c) { return -(P[c + 1] - P[c]); };
@@ -315,7 +316,7 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
     const double e = pm::div_const(pre * M.so_sill_taper[i] * M.so_ek_taper[i], c6, r6);
     double dy = S.yN - yo;
     dy = 0.1 > dy ? 0.1 : dy;
-    const double sl = z[i] / dy, ms = -smax;
+    const double sl = pm::qdiv(z[i], dy), ms = -smax;
     const double mx = (sl >= ms || sl != sl) ? sl : ms;
     double g = sK * mx * sL * M.so_top_taper[i] * M.so_bot_taper[i];
     if (dy > S.yN - S.y0) {

@@ -4,7 +4,7 @@ sys.path.insert(0, '.')
 from pymoc_b200 import configs
 from pymoc_b200.ensemble import Ensemble
 name, M, nt = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
-mk = {'C2': configs.c2_column_so, 'C3': configs.c3_twocol_so, 'C4': configs.c4_jansen_nadeau, 'C5': configs.c5_single_global_basin,
+mk = {'C2': configs.c2_column_so, 'C3': configs.c3_twocol_so, 'C4': configs.c4_jansen_nadeau, 'C5': configs.c5_single_global_basin, 'C5_4096': lambda M: configs.c5_single_global_basin(M, nz=4096, dt_days=0.01, kapfac_max=1.),
       'C1': configs.c1_timestepping}[name]
 spec = mk(M)
 ens = Ensemble(spec)
