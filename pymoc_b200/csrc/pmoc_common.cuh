@@ -80,6 +80,14 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   const int colw = exact ? 4 : 3;  // arrays per column table
   s.w_col[0] = w; w += colw * s.nzp;
   if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += colw * s.nzp; }
+  if (exact) {
+    // psib[nb] + the class counters are live only inside a refresh: they overlay the column tables,
+    // which the kernel re-tabulates from global memory (L2) at the end of every refresh
+    const int psz = s.nbp + s.nbp / 2 + 2;
+    s.w_psib = s.w_col[0];
+    s.w_cnt = s.w_col[0] + s.nbp;
+    if (w - s.w_col[0] < psz) w = s.w_col[0] + psz;
+  }
   if ((flags & PMOC_ISO) && !exact) {
     s.w_remap = w; w += 6 * s.nzp;
     s.w_psib = w; w += s.nbp;
@@ -99,8 +107,6 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     s.w_nweff[1] = w; w += 2 * s.nzp;
     s.w_bb = w; w += s.nzp;
     s.w_pm = w; w += s.nzp;
-    s.w_psib = w; w += s.nbp;
-    s.w_cnt = w; w += s.nbp / 2 + 2;
     s.w_scan = w; w += 10 * 32;
   }
   s.per_warp = w;

@@ -37,6 +37,7 @@ PM_DEV double div_const(double x, double c, double rc) {
 // class of the remap), so they are answered directly: 0 / b = +-0 for any finite non-zero b.
 PM_DEV double qdiv(double a, double b) {
   if (a == 0.0 && b != 0.0 && fabs(b) < INFINITY) return (std::signbit(a) != std::signbit(b)) ? -0.0 : 0.0;
+  if (b == 0.0 && a != 0.0 && a == a) return (std::signbit(a) != std::signbit(b)) ? -INFINITY : INFINITY;
   return a / b;
 }
 
@@ -395,18 +396,25 @@ PM_DEV int bgrid_count_le(const BGrid& G, double v) {
 //   psib[i] = sum_c clip((top_c - bgrid_i)/(top_c - bot_c), 0, 1) * u_c,   u_c = -(Psi[c+1]-Psi[c]),
 // cell c taking its bottom/top buoyancy from column 2 where u_c < 0 and from column 1 otherwise.
 //
-// Fast path (both profiles non-decreasing, which stable stratification and the convective
-// adjustment maintain): for a class value x the cells of column X split into "entirely above
-// x" (clip = 1), "entirely below" (clip = 0) and at most one straddling cell, so
+// Sorted part.  Where a profile is non-decreasing (which stable stratification and the convective
+// adjustment maintain almost everywhere), the cells of column X split for a class value x into
+// "entirely above x" (clip = 1), "entirely below" (clip = 0) and at most one straddling cell, so
 //   psib(x) = sum_X [ S_X[k] + (bX[k] - x) * w_X[k-1] ],   k = #{levels with bX < x},
 // with S_X[k] = sum_{c >= k} [cell c uses X] u_c (a warp suffix scan) and
 // w_X[c] = [cell c uses X] u_c / (bX[c+1] - bX[c]).  O(nb + nz) instead of O(nb nz); the sum is
 // associated differently from np.sum (relative difference ~1e-16).  Flat cells keep the
 // reference's inf/NaN outcomes: (top-x)/0 is +inf -> 1 below the cell, -inf -> 0
-// above it and 0/0 = NaN on it.  Anything else (an inverted cell, a NaN) takes the direct path.
-// k is not searched for: every level drops a count into the class slot where its buoyancy first
-// falls below the class value (integer shared-memory atomics: exact, order independent), and a
-// prefix sum over the classes turns the counts into k for both columns at once.
+// above it and 0/0 = NaN on it.  k is not searched for: every level drops a count into the class
+// slot where its buoyancy first falls below the class value (integer shared-memory atomics: exact,
+// order independent), and a prefix sum over the classes turns the counts into k for both columns.
+//
+// Exceptional cells.  Profiles are not always sorted: the 'jn' bottom condition bbot = b[1] leaves
+// b[0] one rounding above b[1] for many members, and spin-up transients hold inverted layers.  The
+// sorted machinery then runs on the running maximum bX' of each profile (sorted by construction)
+// with the transport of every cell whose end points differ from the running maximum set to zero,
+// and exactly those "exceptional" cells are added class by class with the reference's own
+// expression (the direct O(nb E) loop, E = number of exceptional cells).  A NaN anywhere makes
+// every cell exceptional.
 // Scratch: rs = 6*nzp doubles, psib_s = nb doubles, cnt_s = nb+1 ints, all owned by this warp.
 
 template <int LPL>
@@ -416,8 +424,9 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
   const double psin = rt::shfl_down(psi[0], 1);
   const double b1n = rt::shfl_down(b1[0], 1), b2n = rt::shfl_down(b2[0], 1);
   double lo = INFINITY, hi = -INFINITY;
-  double u[LPL], up1[LPL], up2[LPL];
-  bool unsorted = false;
+  double u[LPL], up1[LPL], up2[LPL], m1[LPL], m2[LPL];
+  bool nan = false;
+  double r1 = -INFINITY, r2 = -INFINITY;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
@@ -431,10 +440,15 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       lo = b2[j] < lo ? b2[j] : lo;
       hi = b1[j] > hi ? b1[j] : hi;
       hi = b2[j] > hi ? b2[j] : hi;
+      nan |= b1[j] != b1[j] || b2[j] != b2[j];
+      r1 = b1[j] > r1 ? b1[j] : r1;
+      r2 = b2[j] > r2 ? b2[j] : r2;
     }
+    m1[j] = r1;
+    m2[j] = r2;
     if (i < nz - 1) {
       u[j] = -((last ? psin : psi[jn]) - psi[j]);
-      unsorted |= !(up1[j] >= b1[j]) || !(up2[j] >= b2[j]) || u[j] != u[j];
+      nan |= u[j] != u[j];
     }
   }
   BGrid G;
@@ -443,21 +457,113 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
   G.nb = nb;
   G.step = (G.hi - G.lo) / (double)(nb - 1);
   G.rstep = 1.0 / G.step;
-  if (rt::ballot(unsorted) == 0) {
+  const bool allexc = rt::ballot(nan) != 0;
+  // running maxima across the lanes (exclusive max-scan of the lane maxima)
+  {
+    double v1 = r1, v2 = r2;
+    PM_UNROLL
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o1 = rt::shfl_up(v1, d), o2 = rt::shfl_up(v2, d);
+      if (L >= d) {
+        v1 = o1 > v1 ? o1 : v1;
+        v2 = o2 > v2 ? o2 : v2;
+      }
+    }
+    double e1 = rt::shfl_up(v1, 1), e2 = rt::shfl_up(v2, 1);
+    if (L == 0) e1 = e2 = -INFINITY;
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      m1[j] = e1 > m1[j] ? e1 : m1[j];
+      m2[j] = e2 > m2[j] ? e2 : m2[j];
+    }
+  }
+  const double m1n = rt::shfl_down(m1[0], 1), m2n = rt::shfl_down(m2[0], 1);
+  // exceptional cells: an end point below the running maximum of the column the cell is taken from
+  unsigned excm = 0;
+  int ne = 0;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    if (i < nz - 1) {
+      const bool last = j == LPL - 1;
+      const int jn = j + 1 < LPL ? j + 1 : j;
+      const bool from2 = u[j] < 0;
+      const double mu = from2 ? (last ? m2n : m2[jn]) : (last ? m1n : m1[jn]);
+      const double upv = from2 ? up2[j] : up1[j];
+      const double mb = from2 ? m2[j] : m1[j], bv = from2 ? b2[j] : b1[j];
+      if (allexc || mu != upv || mb != bv) {
+        excm |= 1u << j;
+        ++ne;
+      }
+    }
+  }
+  int incl = ne;
+  PM_UNROLL
+  for (int d = 1; d < 32; d <<= 1) {
+    const int o = rt::shfl_i(incl, L >= d ? L - d : L);
+    if (L >= d) incl += o;
+  }
+  const int E = rt::shfl_i(incl, 31);
+  if (E > 0) {
+    // the reference's expression, class by class, over the exceptional cells only
+    double *ctop = rs, *crinv = rs + nzp, *cu = rs + 2 * nzp;
+    int pos = incl - ne;
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      if ((excm >> j) & 1u) {
+        const bool from2 = u[j] < 0;
+        const double bot = from2 ? b2[j] : b1[j];
+        const double top = from2 ? up2[j] : up1[j];
+        ctop[pos] = top;
+        crinv[pos] = 1.0 / (top - bot);
+        cu[pos] = u[j];
+        ++pos;
+      }
+    }
+    rt::syncwarp();
+    constexpr int KB = 8;
+    for (int base = 0; base < nb; base += 32 * KB) {
+      double bg[KB], acc[KB];
+      PM_UNROLL
+      for (int k = 0; k < KB; ++k) {
+        const int i = base + k * 32 + L;
+        bg[k] = G.at(i < nb ? i : nb - 1);
+        acc[k] = 0.0;
+      }
+      for (int c = 0; c < E; ++c) {
+        const double top = ctop[c], r = crinv[c], uc = cu[c];
+        PM_UNROLL
+        for (int k = 0; k < KB; ++k) {
+          double t = (top - bg[k]) * r;
+          t = t < 0. ? 0. : t;
+          t = t > 1. ? 1. : t;
+          acc[k] = rt::fma(t, uc, acc[k]);
+        }
+      }
+      PM_UNROLL
+      for (int k = 0; k < KB; ++k) {
+        const int i = base + k * 32 + L;
+        if (i < nb) psib_s[i] = acc[k];
+      }
+    }
+    rt::syncwarp();
+    if (allexc) return G;
+  }
+  {
     double *b1_s = rs, *b2_s = rs + nzp, *w1_s = rs + 2 * nzp, *w2_s = rs + 3 * nzp, *S1_s = rs + 4 * nzp,
            *S2_s = rs + 5 * nzp;
-    // suffix sums of the transports taken from each column
+    // suffix sums of the transports taken from each column (exceptional cells carry none)
     double s1[LPL], s2[LPL];
-    double r1 = 0.0, r2 = 0.0;
+    double q1 = 0.0, q2 = 0.0;
     PM_UNROLL
     for (int j = LPL - 1; j >= 0; --j) {
-      const bool from2 = u[j] < 0;
-      r1 = r1 + (from2 ? 0.0 : u[j]);
-      r2 = r2 + (from2 ? u[j] : 0.0);
-      s1[j] = r1;
-      s2[j] = r2;
+      const bool from2 = u[j] < 0, ex = (excm >> j) & 1u;
+      q1 = q1 + ((from2 || ex) ? 0.0 : u[j]);
+      q2 = q2 + ((from2 && !ex) ? u[j] : 0.0);
+      s1[j] = q1;
+      s2[j] = q2;
     }
-    double t1 = r1, t2 = r2;  // inclusive suffix over lanes
+    double t1 = q1, t2 = q2;  // inclusive suffix over lanes
     PM_UNROLL
     for (int d = 1; d < 32; d <<= 1) {
       const double o1 = rt::shfl_down(t1, d), o2 = rt::shfl_down(t2, d);
@@ -466,18 +572,20 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
         t2 = t2 + o2;
       }
     }
-    const double e1 = t1 - r1, e2 = t2 - r2;  // lanes above this one
+    const double e1 = t1 - q1, e2 = t2 - q2;  // lanes above this one
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
       const int i = lev<LPL>(j);
       if (i < nz) {
-        const bool cell = i < nz - 1, from2 = u[j] < 0;
-        b1_s[i] = b1[j];
-        b2_s[i] = b2[j];
+        const bool last = j == LPL - 1;
+        const int jn = j + 1 < LPL ? j + 1 : j;
+        const bool cell = i < nz - 1 && !((excm >> j) & 1u), from2 = u[j] < 0;
+        b1_s[i] = m1[j];
+        b2_s[i] = m2[j];
         S1_s[i] = s1[j] + e1;
         S2_s[i] = s2[j] + e2;
-        w1_s[i] = (cell && !from2) ? u[j] / (up1[j] - b1[j]) : 0.0;
-        w2_s[i] = (cell && from2) ? u[j] / (up2[j] - b2[j]) : 0.0;
+        w1_s[i] = (cell && !from2) ? u[j] / ((last ? m1n : m1[jn]) - m1[j]) : 0.0;
+        w2_s[i] = (cell && from2) ? u[j] / ((last ? m2n : m2[jn]) - m2[j]) : 0.0;
       }
     }
     rt::syncwarp();
@@ -486,8 +594,8 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
       if (lev<LPL>(j) < nz) {
-        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, b1[j])], 1);
-        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, b2[j])], 1 << 16);
+        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, m1[j])], 1);
+        rt::atomic_add_shared(&cnt_s[bgrid_count_le(G, m2[j])], 1 << 16);
       }
     }
     rt::syncwarp();
@@ -495,17 +603,17 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
     const int i0 = L * cpl < nb ? L * cpl : nb, i1 = i0 + cpl < nb ? i0 + cpl : nb;
     int run = 0;
     for (int i = i0; i < i1; ++i) run += cnt_s[i];
-    int incl = run;
+    int inc2 = run;
     PM_UNROLL
     for (int d = 1; d < 32; d <<= 1) {
-      const int o = rt::shfl_i(incl, L >= d ? L - d : L);
-      if (L >= d) incl += o;
+      const int o = rt::shfl_i(inc2, L >= d ? L - d : L);
+      if (L >= d) inc2 += o;
     }
-    run = incl - run;  // levels counted in the classes of the lanes below
+    run = inc2 - run;  // levels counted in the classes of the lanes below
     for (int i = i0; i < i1; ++i) {
       const double x = G.at(i);
       run += cnt_s[i];
-      const int k1 = run & 0xffff, k2 = run >> 16;  // #{levels with bX < x}
+      const int k1 = run & 0xffff, k2 = run >> 16;  // #{levels with bX' < x}
       double c1 = 0.0, c2 = 0.0;
       if (k1 < nz) {
         const double bk = b1_s[k1];
@@ -523,52 +631,10 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
           for (int c = k2; c + 1 < nz && b2_s[c + 1] == x; ++c)
             if (w2_s[c] != 0.0) c2 = NAN;
       }
-      psib_s[i] = c1 + c2;
+      psib_s[i] = E > 0 ? psib_s[i] + (c1 + c2) : c1 + c2;
     }
     rt::syncwarp();
-    return G;
   }
-  // direct path: every class against every cell
-  double *ctop = rs, *crinv = rs + nzp, *cu = rs + 2 * nzp;
-  PM_UNROLL
-  for (int j = 0; j < LPL; ++j) {
-    const int i = lev<LPL>(j);
-    if (i < nz - 1) {
-      const bool from2 = u[j] < 0;
-      const double bot = from2 ? b2[j] : b1[j];
-      const double top = from2 ? up2[j] : up1[j];
-      ctop[i] = top;
-      crinv[i] = 1.0 / (top - bot);
-      cu[i] = u[j];
-    }
-  }
-  rt::syncwarp();
-  constexpr int KB = 8;
-  for (int base = 0; base < nb; base += 32 * KB) {
-    double bg[KB], acc[KB];
-    PM_UNROLL
-    for (int k = 0; k < KB; ++k) {
-      const int i = base + k * 32 + L;
-      bg[k] = G.at(i < nb ? i : nb - 1);
-      acc[k] = 0.0;
-    }
-    for (int c = 0; c < nz - 1; ++c) {
-      const double top = ctop[c], r = crinv[c], uc = cu[c];
-      PM_UNROLL
-      for (int k = 0; k < KB; ++k) {
-        double t = (top - bg[k]) * r;
-        t = t < 0. ? 0. : t;
-        t = t > 1. ? 1. : t;
-        acc[k] = rt::fma(t, uc, acc[k]);
-      }
-    }
-    PM_UNROLL
-    for (int k = 0; k < KB; ++k) {
-      const int i = base + k * 32 + L;
-      if (i < nb) psib_s[i] = acc[k];
-    }
-  }
-  rt::syncwarp();
   return G;
 }
 
@@ -623,7 +689,7 @@ PM_DEV double interp1(double x, const double* xp, const double* fp, int n) {
   const int j = search_le(xp, n, x);
   if (j == n - 1) return fp[j];
   if (xp[j] == x) return fp[j];
-  const double slope = (fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j]);
+  const double slope = qdiv(fp[j + 1] - fp[j], xp[j + 1] - xp[j]);
   double res = slope * (x - xp[j]) + fp[j];
   if (res != res) {
     res = slope * (x - xp[j + 1]) + fp[j + 1];
@@ -1101,13 +1167,26 @@ PM_DEV double interp_at(double x, const double* xp, const double* fp, int n, int
   if (k == n) return fp[n - 1];
   if (k == n - 1) return fp[k];
   if (xp[k] == x) return fp[k];
-  const double slope = (fp[k + 1] - fp[k]) / (xp[k + 1] - xp[k]);
+  const double slope = qdiv(fp[k + 1] - fp[k], xp[k + 1] - xp[k]);
   double res = slope * (x - xp[k]) + fp[k];
   if (res != res) {
     res = slope * (x - xp[k + 1]) + fp[k + 1];
     if (res != res && fp[k] == fp[k + 1]) res = fp[k];
   }
   return res;
+}
+
+// np.interp(x, xp, fp) for a non-decreasing xp with the index of the previous time step as a first
+// guess: j is the last index with xp[j] <= x (what numpy's search returns for a sorted abscissa
+// whatever its own guess was), so a verified guess and the binary search agree.
+PM_DEV double interp1_guess(double x, const double* xp, const double* fp, int n, int& guess) {
+  if (x != x) return x;
+  if (x > xp[n - 1]) return fp[n - 1];
+  if (x < xp[0]) return fp[0];
+  int j = guess < 0 ? 0 : (guess > n - 2 ? n - 2 : guess);
+  if (!(xp[j] <= x && x < xp[j + 1])) j = search_le(xp, n, x);
+  guess = j;
+  return interp_at(x, xp, fp, n, j);
 }
 
 struct MlState {
@@ -1179,31 +1258,45 @@ PM_DEV void ml_setup(MlState& S, const double* ygrid, int ny, double Ks, double 
   rt::syncwarp();
 }
 
-// (value, index) arg-min with np.argmin's rules: first occurrence, NaN wins.
+// np.argmin(bs): first occurrence of the minimum, a NaN wins (first NaN).  The doubles are mapped to
+// unsigned keys of the same order (-0.0 counted as +0.0, as `<` does) and reduced 32 bits at a time
+// with the warp min-reduction; the lowest point index holding the minimum is the answer.
 PM_DEV int ml_argmin(const MlState& S) {
-  double v = INFINITY;
-  int idx = 0x7fffffff;
+  unsigned hi[kMLP], lo[kMLP];
+  bool nan = false;
   PM_UNROLL
   for (int e = 0; e < kMLP; ++e) {
-    const int k = mlk(e);
-    if (k < S.ny) {
-      const double x = S.bs[e];
-      const bool better = idx == 0x7fffffff || ((x != x) && (v == v)) || x < v;
-      if (better) { v = x; idx = k; }
-    }
+    const double x = S.bs[e] + 0.0;
+    unsigned long long b;
+    static_assert(sizeof(b) == sizeof(x), "binary64");
+    memcpy(&b, &x, 8);
+    b = (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    const bool in = mlk(e) < S.ny;
+    hi[e] = in ? (unsigned)(b >> 32) : 0xffffffffu;
+    lo[e] = in ? (unsigned)b : 0xffffffffu;
+    nan |= in && x != x;
   }
-  for (int msk = 16; msk > 0; msk >>= 1) {
-    const double ov = rt::shfl_xor(v, msk);
-    const int oi = rt::shfl_i(idx, rt::lane() ^ msk);
-    const bool vnan = v != v, onan = ov != ov;
-    bool take;
-    if (oi == 0x7fffffff) take = false;
-    else if (idx == 0x7fffffff) take = true;
-    else if (vnan || onan) take = onan && (!vnan || oi < idx);
-    else take = ov < v || (ov == v && oi < idx);
-    if (take) { v = ov; idx = oi; }
+  if (rt::ballot(nan)) {
+    int first = 0x7fffffff;
+    PM_UNROLL
+    for (int e = kMLP - 1; e >= 0; --e)
+      if (mlk(e) < S.ny && S.bs[e] != S.bs[e]) first = mlk(e);
+    return rt::min_i(first);
   }
-  return idx;
+  unsigned h = hi[0];
+  PM_UNROLL
+  for (int e = 1; e < kMLP; ++e) h = hi[e] < h ? hi[e] : h;
+  const unsigned hmin = rt::min_u(h);
+  unsigned l = 0xffffffffu;
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e)
+    if (hi[e] == hmin && lo[e] < l) l = lo[e];
+  const unsigned lmin = rt::min_u(l);
+  int idx = 0x7fffffff;
+  PM_UNROLL
+  for (int e = kMLP - 1; e >= 0; --e)
+    if (hi[e] == hmin && lo[e] == lmin && mlk(e) < S.ny) idx = mlk(e);
+  return rt::min_i(idx);
 }
 
 PM_DEV void ml_south_bc(MlState& S, double ps1, const double* bb_s, unsigned* status) {
@@ -1234,7 +1327,7 @@ PM_DEV void ml_step(MlState& S, const double* bb_s, const double* pm_s, int nz, 
   if (sorted) {
     PM_UNROLL
     for (int e = 0; e < kMLP; ++e)
-      if (mlk(e) < ny) ps[e] = interp1(S.bs[e], bb_s, pm_s, nz);
+      if (mlk(e) < ny) ps[e] = interp1_guess(S.bs[e], bb_s, pm_s, nz, S.jp[e]);
   } else {
     // PMOC_ST_XP_NONMONOTONE: numpy's search carries its result into the next query as the guess
     // (j_k = search_guess(x_k, j_{k-1}), j_{-1} = 0), and for an unsorted abscissa the answer depends

@@ -183,6 +183,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       apply(iso_b, iso_n, psi_so);
     else
       apply(psi_tw, iso_n, psi_so);
+    if (ML) {  // the remap scratch overlaid the column tables (plan_smem)
+      pm::col_tabulate_exact<LPL>(xb, vrow(M.basin.kappa, m), vrow(M.basin.Area, m), nz, M.basin.nvar);
+      pm::col_tabulate_exact<LPL>(xn, vrow(M.north.kappa, m), vrow(M.north.Area, m), nz, M.north.nvar);
+    }
   };
 
   const long long K = M.K, it_end = a.it0 + a.nsteps;

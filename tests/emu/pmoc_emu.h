@@ -70,6 +70,16 @@ inline int max_i(int v) {
   return m;
 }
 inline int min_i(int v) { return -max_i(-v); }
+inline unsigned min_u(unsigned v) {
+  const unsigned char* all = pmemu::exchange(&v, sizeof(unsigned));
+  unsigned m = v;
+  for (int l = 0; l < 32; ++l) {
+    unsigned x;
+    std::memcpy(&x, all + 16 * l, sizeof(unsigned));
+    if (x < m) m = x;
+  }
+  return m;
+}
 inline void syncwarp() { int z = 0; (void)pmemu::exchange(&z, sizeof(int)); }
 inline void syncblock() { pmemu::block_barrier(); }
 }  // namespace rt
