@@ -236,8 +236,9 @@ PM_DEV void col_nweff(const ExactCol& T, const double (&wA)[LPL], const double* 
 
 template <int LPL>
 PM_DEV void col_step_exact(double (&b)[LPL], const ExactCol& T, int var, const ExactGeo& G, int nz, double dt) {
-  const double* kap = T.kap[var];
-  const double* nweff = T.nweff[var];
+  // (offsets from one base pointer, not a run-time pick between two pointers: the loads stay LDS)
+  const double* kap = T.kap[0] + var * (T.kap[1] - T.kap[0]);
+  const double* nweff = T.nweff[0] + var * (T.nweff[1] - T.nweff[0]);
   const double bnext = rt::shfl_down(b[0], 1);
   double bzu[LPL];
   PM_UNROLL
@@ -669,7 +670,8 @@ PM_DEV double interp_bgrid(double x, const BGrid& G, const double* psib_s) {
 // ===================================================================== Psi_SO
 // index of the last element <= key in a non-decreasing array (numpy binary_search_with_guess
 // result for a key inside the range)
-PM_DEV int search_le(const double* a, int n, double key) {
+template <class XP>
+PM_DEV int search_le(XP a, int n, double key) {
   int lo = 0, hi = n;
   while (lo < hi) {
     const int mid = lo + ((hi - lo) >> 1);
@@ -1125,7 +1127,8 @@ constexpr int kMaxNyMl = 32 * kMLP;
 // statement.  For a sorted `arr` the result does not depend on `guess`; for an unsorted
 // one (np.interp with a non-monotone b_basin as abscissa) it does, and the
 // reference's answer is reproduced only by carrying the guess from query to query.
-PM_DEV int search_guess(double key, const double* arr, int len, int guess) {
+template <class XP>
+PM_DEV int search_guess(double key, XP arr, int len, int guess) {
   constexpr int kLikelyInCache = 8;
   int imin = 0, imax = len;
   if (key > arr[len - 1]) return len;
@@ -1161,7 +1164,8 @@ PM_DEV int search_guess(double key, const double* arr, int len, int guess) {
 }
 
 // value of np.interp(x, xp, fp) once arr_interp's search has returned index k
-PM_DEV double interp_at(double x, const double* xp, const double* fp, int n, int k) {
+template <class XP>
+PM_DEV double interp_at(double x, XP xp, const double* fp, int n, int k) {
   if (x != x) return x;
   if (k == -1) return fp[0];
   if (k == n) return fp[n - 1];
@@ -1179,15 +1183,33 @@ PM_DEV double interp_at(double x, const double* xp, const double* fp, int n, int
 // np.interp(x, xp, fp) for a non-decreasing xp with the index of the previous time step as a first
 // guess: j is the last index with xp[j] <= x (what numpy's search returns for a sorted abscissa
 // whatever its own guess was), so a verified guess and the binary search agree.
-PM_DEV double interp1_guess(double x, const double* xp, const double* fp, int n, int& guess) {
+template <class XP>
+PM_DEV double interp1_guess(double x, XP xp, const double* fp, int n, int& guess) {
   if (x != x) return x;
-  if (x > xp[n - 1]) return fp[n - 1];
+  if (x >= xp[n - 1]) return fp[n - 1];  // x == xp[n-1]: the search returns n-1 and arr_interp returns fp[n-1]
   if (x < xp[0]) return fp[0];
   int j = guess < 0 ? 0 : (guess > n - 2 ? n - 2 : guess);
-  if (!(xp[j] <= x && x < xp[j + 1])) j = search_le(xp, n, x);
+  if (!(xp[j] <= x && x < xp[j + 1])) {
+    // the state drifts: try the two neighbouring intervals before searching
+    const int up = j + 1 < n - 1 ? j + 1 : j, dn = j > 0 ? j - 1 : 0;
+    if (xp[up] <= x && x < xp[up + 1])
+      j = up;
+    else if (xp[dn] <= x && x < xp[dn + 1])
+      j = dn;
+    else
+      j = search_le(xp, n, x);
+  }
   guess = j;
   return interp_at(x, xp, fp, n, j);
 }
+
+// natural-order array stored with one pad word after every 2^sh entries (conflict-free for writers that
+// own 2^sh consecutive entries each); reads like a pointer
+struct PadIdx {
+  const double* p;
+  int sh;
+  PM_DEV double operator[](int i) const { return p[i + (i >> sh)]; }
+};
 
 struct MlState {
   double bs[kMLP];                            // surface buoyancy of the lane's points
@@ -1203,6 +1225,50 @@ struct MlState {
 };
 
 PM_DEV int mlk(int e) { return rt::lane() * kMLP + e; }
+
+// MlState <-> shared memory (kMlSave doubles owned by the warp), for kernels whose mixed-layer warp
+// also carries column state in registers: the mixed layer is parked between its steps.
+constexpr int kMlSave = 16 * 32 + 12;
+PM_DEV void ml_park(const MlState& S, double* sm, bool all) {
+  const int Ln = rt::lane();
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    sm[(0 + e) * 32 + Ln] = S.bs[e];
+    sm[(2 + e) * 32 + Ln] = (double)S.jp[e];
+    sm[(4 + e) * 32 + Ln] = S.ps[e];
+    if (all) {
+      sm[(6 + e) * 32 + Ln] = S.a[e];
+      sm[(8 + e) * 32 + Ln] = S.m[e];
+      sm[(10 + e) * 32 + Ln] = S.sfh[e];
+      sm[(12 + e) * 32 + Ln] = S.rv[e];
+      sm[(14 + e) * 32 + Ln] = S.brest[e];
+    }
+  }
+  if (all && Ln == 0) {
+    double* u = sm + 16 * 32;
+    u[0] = S.shalf; u[1] = S.sdiag; u[2] = S.h; u[3] = S.rh; u[4] = S.L; u[5] = S.rL; u[6] = S.dy; u[7] = S.rdy;
+    u[8] = (double)S.ny; u[9] = (double)S.first_pos;
+  }
+  rt::syncwarp();
+}
+PM_DEV void ml_unpark(MlState& S, const double* sm, const double* scan) {
+  const int Ln = rt::lane();
+  PM_UNROLL
+  for (int e = 0; e < kMLP; ++e) {
+    S.bs[e] = sm[(0 + e) * 32 + Ln];
+    S.jp[e] = (int)sm[(2 + e) * 32 + Ln];
+    S.ps[e] = sm[(4 + e) * 32 + Ln];
+    S.a[e] = sm[(6 + e) * 32 + Ln];
+    S.m[e] = sm[(8 + e) * 32 + Ln];
+    S.sfh[e] = sm[(10 + e) * 32 + Ln];
+    S.rv[e] = sm[(12 + e) * 32 + Ln];
+    S.brest[e] = sm[(14 + e) * 32 + Ln];
+  }
+  const double* u = sm + 16 * 32;
+  S.shalf = u[0]; S.sdiag = u[1]; S.h = u[2]; S.rh = u[3]; S.L = u[4]; S.rL = u[5]; S.dy = u[6]; S.rdy = u[7];
+  S.ny = (int)u[8]; S.first_pos = (int)u[9];
+  S.scan = scan;
+}
 
 // State-independent part of SO_ML: flux factors and the factorisation of the Crank-Nicolson
 // matrix (SO_ML.py:155-165, 191-196).  inv(U).V.bs is evaluated as a Thomas solve whose two
@@ -1299,7 +1365,8 @@ PM_DEV int ml_argmin(const MlState& S) {
   return rt::min_i(idx);
 }
 
-PM_DEV void ml_south_bc(MlState& S, double ps1, const double* bb_s, unsigned* status) {
+template <class XP>
+PM_DEV void ml_south_bc(MlState& S, double ps1, XP bb_s, unsigned* status) {
   // SO_ML.py:93-98
   if (rt::lane() == 0) {
     if (ps1 > 0) {
@@ -1316,7 +1383,8 @@ PM_DEV void ml_south_bc(MlState& S, double ps1, const double* bb_s, unsigned* st
 // SO_ML.advdiff (SO_ML.py:228-274) for one step.  bb_s: b_basin, pm_s: Psi_mod (Psi_b with the
 // leading zeros replaced, SO_ML.py:228-230), both natural order in shared memory; bs_s: scratch
 // [ny] of this warp.  `sorted`: b_basin is non-decreasing (warp-uniform).
-PM_DEV void ml_step(MlState& S, const double* bb_s, const double* pm_s, int nz, bool sorted, double* bs_s, double dt,
+template <class XP>
+PM_DEV void ml_step(MlState& S, XP bb_s, const double* pm_s, int nz, bool sorted, double* bs_s, double dt,
                     unsigned* status) {
   const int ny = S.ny, Ln = rt::lane();
   PM_UNROLL

@@ -84,6 +84,14 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
   const int nz = m->nz, ny = m->ny, nb = m->nb;
   const unsigned f = m->flags;
   Mirror mr;
+  {  // keep the stream-ordered pool's memory between calls (the default trims it at every synchronisation)
+    int dev = 0;
+    cudaMemPool_t pool;
+    unsigned long long keep = ~0ull;
+    PM_CUDA_OK(cudaGetDevice(&dev));
+    PM_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    PM_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   PM_CUDA_OK(cudaStreamCreateWithFlags(&mr.s, cudaStreamNonBlocking));
   pmoc_model d = *m;
   const bool carry = it0 > 0;  // streamfunctions diagnosed by an earlier call are inputs

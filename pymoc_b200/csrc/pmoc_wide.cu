@@ -2,15 +2,15 @@
 // topology of examples/run_single_global_basin.py / run_JansenNadeau_2018.py (two convecting
 // columns, thermal wind with isopycnal remap, explicit Psi_SO, SO_ML).
 //
-// One CTA owns one member.  k_wide_steps keeps both buoyancy profiles, the cell gradients and
-// Psi_mod in shared memory for all the steps of a launch and streams the per-level constants
-// (geometry, kappa, -weff, Area) from a caller-provided scratch buffer that stays L2 resident;
-// the arithmetic is the bit-faithful step of pm::col_step_exact, level by level.  At the stable
-// time step of such grids the streamfunctions are re-diagnosed once in tens of thousands of steps
-// (K = 72 000 at nz = 4096), so the diagnosis is a separate, plain kernel (k_wide_refresh) and the
-// host loop in run_model_wide alternates the two.  First correct version: the constants are
-// re-read every step instead of being register/shared resident.
+// One CTA owns one member.  k_wide_steps2 keeps both buoyancy profiles and the geometry of the
+// thread's levels in registers and -weff / kappa in shared memory for all the steps of a launch (see
+// the comment on the kernel); the arithmetic is the bit-faithful step of pm::col_step_exact, level
+// by level.  At the stable time step of such grids the streamfunctions are re-diagnosed once in tens
+// of thousands of steps (K = 72 000 at nz = 4096), so the diagnosis is a separate, plain kernel
+// (k_wide_refresh) and the host loop in pmoc_run_model_wide alternates the two.
 #include "pmoc_common.cuh"
+
+#include <type_traits>
 
 namespace pmk {
 
@@ -332,22 +332,44 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
   if (t == 0 && M.status) M.status[m] |= all;
 }
 
-// ---- the steps ----------------------------------------------------------------------------------
-PM_GLOBAL void k_wide_steps(WideArgs a) {
+// ---- the steps, state and per-level constants resident on chip ---------------------------------
+// 256 column threads own LPT consecutive levels each (both columns): the buoyancies, dz, 1/dz and
+// 1/dzc of those levels stay in registers for the whole launch; -weff and kappa of the variant in
+// use live in shared memory in owner-major order (slot j*256 + t: conflict free, re-read from the
+// scratch buffer by their owner when a boundary switch flips the variant).  What the neighbours and
+// the mixed layer need is published once per step: the basin profile in natural order with one pad
+// word per LPT levels (conflict-free stores, read through pm::PadIdx) and the first/last northern
+// level of every thread.  The last warp also runs SO_ML, whose state is parked in shared memory
+// between its steps (the register file is full of column state: 8 warps x 255 registers); three
+// block barriers per step.  The arithmetic is the bit-faithful step of pm::col_step_exact.
+constexpr int kWideCol = 256;
+constexpr int kWideAll = kWideCol;
+
+template <int LPT, int SH>
+PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
+  static_assert((1 << SH) == LPT && LPT >= 2, "LPT = 2^SH >= 2");
   const pmoc_model& M = a.m;
-  const int nz = M.nz, ny = M.ny, T = wnthr(), t = wtid(), W = rt::warp_in_block();
+  const int nz = M.nz, ny = M.ny, t = wtid(), W = rt::warp_in_block(), Ln = rt::lane();
+  const bool col = t < kWideCol, mlw = W == kWideCol / 32 - 1;
   const long long m = rt::block_idx();
   const double dt = M.dt;
-  double* sm = rt::smem();
-  double *bb = sm, *bn = sm + nz, *gzb = sm + 2 * nz, *gzn = sm + 3 * nz, *pm_s = sm + 4 * nz;
+  constexpr int nzp = kWideCol * LPT;
   const int nyp = (ny + 3) & ~3;
-  double* bs_s = sm + 5 * nz;
+  double* sm = rt::smem();
+  double *nwb = sm, *nwn = sm + nzp, *kb = sm + 2 * nzp, *kn = sm + 3 * nzp;
+  double* bbp = sm + 4 * nzp;            // basin profile, padded natural order: nzp + kWideCol
+  double* pm_s = bbp + nzp + kWideCol;   // Psi_mod, natural order
+  double* bne = pm_s + nzp;              // north: first/last level of every thread, [2*kWideCol] = level 1
+  double* bs_s = bne + 2 * kWideCol + 2;
   double* scan_s = bs_s + nyp;
   double* ysm = scan_s + 320;
-  double* dbox = ysm + nyp;                          // 8 doubles of broadcast space
-  int* ibox = reinterpret_cast<int*>(dbox + 8);      // 8 ints
+  double* dbox = ysm + nyp;                           // [0] = bs[0] of the mixed layer
+  int* ibox = reinterpret_cast<int*>(dbox + 8);       // 2 x 8 step flags, then 4 ints for the block collectives
+  int* cbox = ibox + 16;
+  double* mlp = dbox + 8 + 10;                        // parked mixed layer, pm::kMlSave
+  const pm::PadIdx bbx{bbp, SH};
   const double* z = M.z;
-  const double *dzu = a.geo, *rdzu = a.geo + nz, *dzc = a.geo + 2 * nz, *rdzc = a.geo + 3 * nz;
+  const int lo = t * LPT;
   double* mem = a.memb + (size_t)m * 6 * nz;
   double *nwb0 = mem, *nwb1 = mem + nz, *nwn0 = mem + 2 * nz, *nwn1 = mem + 3 * nz, *rab = mem + 4 * nz,
          *ran = mem + 5 * nz;
@@ -360,146 +382,272 @@ PM_GLOBAL void k_wide_steps(WideArgs a) {
   const int nvb = M.basin.nvar > 1 ? nz : 0, nvn = M.north.nvar > 1 ? nz : 0;  // offset of variant 1
   unsigned status = 0;
 
-  // state and what the carried streamfunctions imply (run_JansenNadeau_2018.py:228-231)
+  int var_b = (M.basin.var && M.basin.nvar > 1) ? M.basin.var[m] : 0;
+  int var_n = (M.north.var && M.north.nvar > 1) ? M.north.var[m] : 0;
+  double bbot_b = M.basin.bbot[m], bbot_n = M.north.bbot[m];
+  const double bs_b = vat(M.basin.bs, m), bs_n = vat(M.north.bs, m);
+  const double n2_b = vat(M.basin.N2min, m), n2_n = vat(M.north.N2min, m);
+
+  // ---- load: state, geometry, tables ----
+  double bb[LPT], bn[LPT], dzu[LPT], rdzu[LPT], rdzc[LPT];
+  double dzu_m = 1., rdzu_m = 1.;  // cell below the thread's first level
   int fnz = 0x7fffffff, fpos = 0x7fffffff;
-  for (int i = t; i < nz; i += T) {
-    bb[i] = M.basin.b[m * nz + i];
-    bn[i] = M.north.b[m * nz + i];
-    const double pso = M.Psi_so[m * nz + i], ib = M.Psi_iso_b[m * nz + i], in_ = M.Psi_iso_n[m * nz + i];
-    pm_s[i] = pso;
-    if (pso != 0.0 && i < fnz) fnz = i;
-    if (pso > 0.0 && i < fpos) fpos = i;
-    const bool in = i >= 1 && i < nz - 1;
-    const double wAb = (ib - pso) * 1e6, wAn = -in_ * 1e6;
-    nwb0[i] = in ? -(wAb - dakb[i]) : 0.0;
-    nwb1[i] = in ? -(wAb - dakb[nvb + i]) : 0.0;
-    nwn0[i] = in ? -(wAn - dakn[i]) : 0.0;
-    nwn1[i] = in ? -(wAn - dakn[nvn + i]) : 0.0;
-    rab[i] = 1.0 / (in ? Ab[i] : 1.0);
-    ran[i] = 1.0 / (in ? An[i] : 1.0);
+  bool areas_differ = false;
+  PM_UNROLL
+  for (int j = 0; j < LPT; ++j) {
+    const int i = lo + j;
+    bb[j] = bn[j] = 0.;
+    dzu[j] = rdzu[j] = rdzc[j] = 1.;
+    {  // boundary and padding levels: zero -weff and kappa make their update an exact no-op
+      const int s = j * kWideCol + t;
+      nwb[s] = nwn[s] = kb[s] = kn[s] = 0.0;
+    }
+    if (col && i < nz) {
+      bb[j] = M.basin.b[m * nz + i];
+      bn[j] = M.north.b[m * nz + i];
+      dzu[j] = a.geo[i];
+      rdzu[j] = a.geo[nz + i];
+      rdzc[j] = a.geo[3 * nz + i];
+      const double pso = M.Psi_so[m * nz + i], ib = M.Psi_iso_b[m * nz + i], in_ = M.Psi_iso_n[m * nz + i];
+      pm_s[i] = pso;
+      if (pso != 0.0 && i < fnz) fnz = i;
+      if (pso > 0.0 && i < fpos) fpos = i;
+      const bool in = i >= 1 && i < nz - 1;
+      const double wAb = (ib - pso) * 1e6, wAn = -in_ * 1e6;
+      const double b0 = in ? -(wAb - dakb[i]) : 0.0, b1 = in ? -(wAb - dakb[nvb + i]) : 0.0;
+      const double n0 = in ? -(wAn - dakn[i]) : 0.0, n1 = in ? -(wAn - dakn[nvn + i]) : 0.0;
+      nwb0[i] = b0; nwb1[i] = b1; nwn0[i] = n0; nwn1[i] = n1;
+      const int s = j * kWideCol + t;
+      nwb[s] = var_b ? b1 : b0;
+      nwn[s] = var_n ? n1 : n0;
+      kb[s] = in ? kapb[(var_b ? nvb : 0) + i] : 0.0;
+      kn[s] = in ? kapn[(var_n ? nvn : 0) + i] : 0.0;
+      if (in) areas_differ |= Ab[i] != Ab[1] || An[i] != An[1];
+      rab[i] = 1.0 / Ab[i];
+      ran[i] = 1.0 / An[i];
+    }
   }
-  for (int i = t; i < nyp; i += T) ysm[i] = M.y[i < ny ? i : ny - 1];
-  fnz = block_min(fnz, ibox);
-  fpos = block_min(fpos, ibox);
+  if (col && lo >= 1 && lo - 1 < nz) {
+    dzu_m = a.geo[lo - 1];
+    rdzu_m = a.geo[nz + lo - 1];
+  }
+  for (int i = t; i < nyp; i += kWideAll) ysm[i] = M.y[i < ny ? i : ny - 1];
+  fnz = block_min(fnz, cbox);
+  fpos = block_min(fpos, cbox);
+  const bool uniA = !block_any(areas_differ, cbox);
+  const double A_b = Ab[1], rA_b = 1.0 / A_b, A_n = An[1], rA_n = 1.0 / A_n;
   const double psi_so1 = M.Psi_so[m * nz + 1], res_b1 = M.Psi_iso_b[m * nz + 1], res_n1 = M.Psi_iso_n[m * nz + 1];
   if (fnz == 0x7fffffff) status |= PMOC_ST_ML_INDEX;
   const double held = pm_s[fnz == 0x7fffffff ? 0 : fnz];
   rt::syncblock();
-  for (int i = t; i < nz && i < fnz; i += T) pm_s[i] = held;
-  rt::syncblock();
+  for (int i = t; i < nz && i < fnz; i += kWideAll) pm_s[i] = held;
 
-  pm::MlState ml{};
-  if (W == 0) {
+  if (mlw) {
+    pm::MlState ml{};
     pm::ml_setup(ml, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m), vrow(M.ml_surflux, m),
                  vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), dt, scan_s);
     ml.first_pos = fpos == 0x7fffffff ? -1 : fpos;
     PM_UNROLL
     for (int e = 0; e < pm::kMLP; ++e) ml.bs[e] = M.ml_bs[m * ny + (pm::mlk(e) < ny ? pm::mlk(e) : ny - 1)];
-    if (t == 0) dbox[4] = ml.bs[0];
+    if (Ln == 0) {
+      dbox[0] = ml.bs[0];
+      for (int k = 0; k < 16; ++k) ibox[k] = (k & 7) == 2 || (k & 7) == 3 ? -1 : 0;
+    }
+    pm::ml_park(ml, mlp, true);
   }
-  double bbot_b = M.basin.bbot[m], bbot_n = M.north.bbot[m];
-  int var_b = (M.basin.var && M.basin.nvar > 1) ? M.basin.var[m] : 0;
-  int var_n = (M.north.var && M.north.nvar > 1) ? M.north.var[m] : 0;
-  const double bs_b = vat(M.basin.bs, m), bs_n = vat(M.north.bs, m);
-  const double n2_b = vat(M.basin.N2min, m), n2_n = vat(M.north.N2min, m);
   rt::syncblock();
 
-  for (long long it = 0; it < a.nsteps; ++it) {
-    // bottom boundary condition and bottom-boundary-layer kappa (run_JansenNadeau_2018.py:233-254)
-    {
-      const double bb0 = bb[0], bb1 = bb[1], nb0 = bn[0], nb1 = bn[1], bs0 = dbox[4];
-      if (psi_so1 < 0) { bbot_b = bs0; var_b = 1; }
-      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; var_b = 1; }
-      else if (psi_so1 >= 0) { bbot_b = bb1; var_b = 0; }
-      if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; var_n = 1; }
-      else { bbot_n = nb1; var_n = 0; }
-      if (M.basin.nvar < 2) var_b = 0;
-      if (M.north.nvar < 2) var_n = 0;
-    }
-    // convective adjustment of both columns (column.py:264-271)
+  // publish the state and the flags the next step needs (buffer q): what the neighbours read, whether
+  // anything convects and the highest stable level (column.py:264-267), whether b_basin is sorted
+  bool mine_b = false, mine_n = false;  // the thread's own levels hold something that convects
+  const bool full = lo + LPT <= nz, owns_top = lo <= nz - 1 && nz - 1 < lo + LPT;
+  double* const bbo = bbp + t * (LPT + 1);  // = &bbp[pad(lo)]: pad(lo + j) = lo + j + t
+  auto publish_as = [&](int q, auto FULL) {
+    constexpr bool fl = decltype(FULL)::value;
     int topb = -1, topn = -1;
-    bool anyb = false, anyn = false;
-    for (int i = t; i < nz; i += T) {
-      if (bb[i] > bs_b) anyb = true; else topb = i;
-      if (bn[i] > bs_n) anyn = true; else topn = i;
-    }
-    rt::syncblock();  // everyone has read bb[0..1] / bn[0..1] for the switches
-    if (t == 0) { ibox[0] = 0; ibox[1] = 0; ibox[2] = -1; ibox[3] = -1; }
-    rt::syncblock();
-    {
-      const unsigned mb = rt::ballot(anyb), mn = rt::ballot(anyn);
-      const int wb = rt::max_i(topb), wn = rt::max_i(topn);
-      if (rt::lane() == 0) {
-        if (mb) rt::atomic_add_shared(&ibox[0], 1);
-        if (mn) rt::atomic_add_shared(&ibox[1], 1);
-        rt::atomic_max_shared(&ibox[2], wb);
-        rt::atomic_max_shared(&ibox[3], wn);
+    bool anyb = false, anyn = false, bad = false;
+    PM_UNROLL
+    for (int j = 0; j < LPT; ++j) {
+      const int i = lo + j;
+      if (fl || i < nz) {
+        bbo[j] = bb[j];
+        if (bb[j] > bs_b) anyb = true; else topb = i;
+        if (bn[j] > bs_n) anyn = true; else topn = i;
+        if (j + 1 < LPT && (fl || i + 1 < nz)) bad |= !(bb[j + 1 < LPT ? j + 1 : j] >= bb[j]);
       }
     }
-    rt::syncblock();
-    {
-      const bool cvb = ibox[0] != 0, cvn = ibox[1] != 0;
-      const double zcb = z[ibox[2] >= 0 ? ibox[2] : 0], zcn = z[ibox[3] >= 0 ? ibox[3] : 0];
-      for (int i = t; i < nz; i += T) {
-        if (cvb) { if (bb[i] > bs_b) bb[i] = bs_b + n2_b * (z[i] - zcb); }
-        else if (i == nz - 1) bb[i] = bs_b;
-        if (cvn) { if (bn[i] > bs_n) bn[i] = bs_n + n2_n * (z[i] - zcn); }
-        else if (i == nz - 1) bn[i] = bs_n;
+    mine_b = anyb;
+    mine_n = anyn;
+    const double upb = rt::shfl_down(bb[0], 1);  // first level of the next thread (same warp)
+    if (Ln < 31 && lo + LPT < nz) bad |= !(upb >= bb[LPT - 1]);
+    bne[2 * t] = bn[0];
+    bne[2 * t + 1] = bn[LPT - 1];
+    if (t == 0) bne[2 * kWideCol] = bn[1];
+    const unsigned mb = rt::ballot(anyb), mn = rt::ballot(anyn), mu = rt::ballot(bad);
+    const int wb = rt::max_i(topb), wn = rt::max_i(topn);
+    if (Ln == 0) {
+      int* f = ibox + 8 * q;
+      if (mb) rt::atomic_add_shared(&f[0], 1);
+      if (mn) rt::atomic_add_shared(&f[1], 1);
+      rt::atomic_max_shared(&f[2], wb);
+      rt::atomic_max_shared(&f[3], wn);
+      if (mu) rt::atomic_or_shared(&f[4], 1);
+    }
+  };
+  auto publish = [&](int q) {
+    if (rt::ballot(!full) == 0)
+      publish_as(q, std::true_type{});
+    else
+      publish_as(q, std::false_type{});
+  };
+  publish(0);
+  rt::syncblock();
+
+  int p = 0;
+  for (long long it = 0; it < a.nsteps; ++it, p ^= 1) {
+    if (col) {
+      // bottom boundary condition and bottom-boundary-layer kappa (run_JansenNadeau_2018.py:233-254);
+      // every thread evaluates the switches from the published values
+      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
+      int vb = var_b, vn = var_n;
+      if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
+      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
+      else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
+      if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
+      else { bbot_n = nb1; vn = 0; }
+      if (M.basin.nvar < 2) vb = 0;
+      if (M.north.nvar < 2) vn = 0;
+      if (vb != var_b) {  // the owner re-reads its levels of the other variant
+        var_b = vb;
+        PM_UNROLL
+        for (int j = 0; j < LPT; ++j) {
+          const int i = lo + j, s = j * kWideCol + t;
+          if (i < nz) {
+            nwb[s] = vb ? nwb1[i] : nwb0[i];
+            kb[s] = (i >= 1 && i < nz - 1) ? kapb[(vb ? nvb : 0) + i] : 0.0;
+          }
+        }
+      }
+      if (vn != var_n) {
+        var_n = vn;
+        PM_UNROLL
+        for (int j = 0; j < LPT; ++j) {
+          const int i = lo + j, s = j * kWideCol + t;
+          if (i < nz) {
+            nwn[s] = vn ? nwn1[i] : nwn0[i];
+            kn[s] = (i >= 1 && i < nz - 1) ? kapn[(vn ? nvn : 0) + i] : 0.0;
+          }
+        }
+      }
+      // convective adjustment (column.py:264-271) of the own levels and of the two neighbour values
+      const int* f = ibox + 8 * p;
+      const bool cvb = f[0] != 0, cvn = f[1] != 0;
+      const double zcb = z[f[2] >= 0 ? f[2] : 0], zcn = z[f[3] >= 0 ? f[3] : 0];
+      auto adj = [&](double v, int i, bool cv, double bs, double n2, double zc) {
+        if (cv) return v > bs ? bs + n2 * (z[i] - zc) : v;
+        return i == nz - 1 ? bs : v;
+      };
+      if ((cvb && mine_b) || (cvn && mine_n) || owns_top) {
+        PM_UNROLL
+        for (int j = 0; j < LPT; ++j) {
+          const int i = lo + j;
+          if (i < nz) {
+            bb[j] = adj(bb[j], i, cvb, bs_b, n2_b, zcb);
+            bn[j] = adj(bn[j], i, cvn, bs_n, n2_n, zcn);
+          }
+        }
       }
       if (t == 0) {  // column.py:232
         bb[0] = bbot_b;
         bn[0] = bbot_n;
       }
-    }
-    rt::syncblock();
-    // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact
-    for (int i = t; i < nz - 1; i += T) {
-      gzb[i] = pm::div_const(bb[i + 1] - bb[i], dzu[i], rdzu[i]);
-      gzn[i] = pm::div_const(bn[i + 1] - bn[i], dzu[i], rdzu[i]);
-    }
-    rt::syncblock();
-    {
-      const double* nwb = var_b ? nwb1 : nwb0;
-      const double* nwn = var_n ? nwn1 : nwn0;
-      const double* kb = kapb + (var_b ? nvb : 0);
-      const double* kn = kapn + (var_n ? nvn : 0);
-      bool bad = false;
-      for (int i = t; i < nz; i += T) {
-        if (i >= 1 && i < nz - 1) {
-          {
-            const double up = gzb[i], dn = gzb[i - 1];
-            const double bzz = pm::div_const(up - dn, dzc[i], rdzc[i]);
-            const double nw = nwb[i], sel = nw > 0 ? up : dn;
-            const double adv = pm::div_const(nw * sel, Ab[i], rab[i]);
-            bb[i] = bb[i] + dt * (adv + kb[i] * bzz);
+      double gpb = 0., gpn = 0.;  // gradient of the cell below the current level
+      if (lo >= 1 && lo < nz) {
+        const double vb_ = adj(bbx[lo - 1], lo - 1, cvb, bs_b, n2_b, zcb);
+        const double vn_ = adj(bne[2 * (t - 1) + 1], lo - 1, cvn, bs_n, n2_n, zcn);
+        gpb = pm::div_const(bb[0] - vb_, dzu_m, rdzu_m);
+        gpn = pm::div_const(bn[0] - vn_, dzu_m, rdzu_m);
+      }
+      double ub = 0., un = 0.;  // level above the thread's last one
+      if (lo + LPT < nz) {
+        ub = adj(bbx[lo + LPT], lo + LPT, cvb, bs_b, n2_b, zcb);
+        un = adj(bne[2 * (t + 1)], lo + LPT, cvn, bs_n, n2_n, zcn);
+      }
+      // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact.  No level tests: at
+      // the boundary and padding levels -weff = kappa = 0 and every operand is finite, so b + dt*0 = b.
+      auto step = [&](auto UA) {
+        constexpr bool ua = decltype(UA)::value;
+        PM_UNROLL
+        for (int j = 0; j < LPT; ++j) {
+          const int s = j * kWideCol + t;
+          const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
+          const double upn = j + 1 < LPT ? bn[j + 1 < LPT ? j + 1 : j] : un;
+          const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+          const double gn = pm::div_const(upn - bn[j], dzu[j], rdzu[j]);
+          const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
+          double Ai_b = A_b, rAi_b = rA_b, Ai_n = A_n, rAi_n = rA_n;
+          if (!ua) {
+            const int i = lo + j < nz ? lo + j : nz - 1;
+            Ai_b = Ab[i]; rAi_b = rab[i]; Ai_n = An[i]; rAi_n = ran[i];
           }
           {
-            const double up = gzn[i], dn = gzn[i - 1];
-            const double bzz = pm::div_const(up - dn, dzc[i], rdzc[i]);
-            const double nw = nwn[i], sel = nw > 0 ? up : dn;
-            const double adv = pm::div_const(nw * sel, An[i], ran[i]);
-            bn[i] = bn[i] + dt * (adv + kn[i] * bzz);
+            const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+            const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+            const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
+            bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
           }
+          {
+            const double bzz = pm::div_const(gn - gpn, dzc, rdzc[j]);
+            const double nw = nwn[s], sel = nw > 0 ? gn : gpn;
+            const double adv = pm::div_const(nw * sel, Ai_n, rAi_n);
+            bn[j] = bn[j] + dt * (adv + kn[s] * bzz);
+          }
+          gpb = gb;
+          gpn = gn;
         }
-      }
-      rt::syncblock();
-      for (int i = t; i < nz - 1; i += T) bad |= !(bb[i + 1] >= bb[i]);
-      const bool sorted = !block_any(bad, ibox);
-      if (W == 0) {
-        pm::ml_step(ml, bb, pm_s, nz, sorted, bs_s, dt, &status);
-        if (t == 0) dbox[4] = ml.bs[0];
-      }
-      rt::syncblock();
+      };
+      if (uniA)
+        step(std::true_type{});
+      else
+        step(std::false_type{});
     }
+    rt::syncblock();  // every neighbour value of this step has been read
+    publish(p ^ 1);
+    rt::syncblock();
+    if (mlw) {
+      // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
+      bool bad = ibox[8 * (p ^ 1) + 4] != 0;
+      const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
+      if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
+      const bool sorted = rt::ballot(bad) == 0;
+      pm::MlState ml;
+      pm::ml_unpark(ml, mlp, scan_s);
+      pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+      pm::ml_park(ml, mlp, false);
+      if (Ln == 0) {
+        dbox[0] = ml.bs[0];
+        int* f = ibox + 8 * p;  // read during this step; refilled by the publish of the next one
+        f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
+      }
+    }
+    rt::syncblock();
   }
 
-  for (int i = t; i < nz; i += T) {
-    M.basin.b[m * nz + i] = bb[i];
-    M.north.b[m * nz + i] = bn[i];
-  }
   bool nan = false;
-  for (int i = t; i < nz; i += T) nan |= !(fabs(bb[i]) <= 1.79e308) || !(fabs(bn[i]) <= 1.79e308);
-  if (W == 0) {
+  if (col) {
+    PM_UNROLL
+    for (int j = 0; j < LPT; ++j) {
+      const int i = lo + j;
+      if (i < nz) {
+        M.basin.b[m * nz + i] = bb[j];
+        M.north.b[m * nz + i] = bn[j];
+        nan |= !(fabs(bb[j]) <= 1.79e308) || !(fabs(bn[j]) <= 1.79e308);
+      }
+    }
+  }
+  if (mlw) {
+    pm::MlState ml;
+    pm::ml_unpark(ml, mlp, scan_s);
     PM_UNROLL
     for (int e = 0; e < pm::kMLP; ++e) {
       const int k = pm::mlk(e);
@@ -510,24 +658,25 @@ PM_GLOBAL void k_wide_steps(WideArgs a) {
       }
     }
   }
-  if (block_any(nan, ibox)) status |= PMOC_ST_NAN;
+  if (block_any(nan, cbox)) status |= PMOC_ST_NAN;
   if (t == 0) {
     M.basin.bbot[m] = bbot_b;
     M.north.bbot[m] = bbot_n;
     if (M.basin.var) M.basin.var[m] = var_b;
     if (M.north.var) M.north.var[m] = var_n;
   }
-  const unsigned all = block_or(status, ibox);  // warp 0 carries the mixed layer's bits
+  const unsigned all = block_or(status, cbox);  // the mixed-layer warp carries SO_ML's bits
   if (t == 0 && M.status) M.status[m] |= all;
+}
+
+size_t wide_steps2_smem(int lpt, int ny) {
+  const int nyp = (ny + 3) & ~3, nzp = kWideCol * lpt;
+  return sizeof(double) * (size_t)(6 * nzp + kWideCol + 2 * kWideCol + 2 + 2 * nyp + 320 + 8 + 10 + pm::kMlSave);
 }
 
 size_t wide_refresh_smem(int nz, int ny, int nb) {
   const int nbp = (nb + 3) & ~3, nyp = (ny + 3) & ~3;
   return sizeof(double) * (size_t)(6 * nz + nbp + nbp / 2 + 2 + 64 + kWideThreads + 3 * nyp + 4);
-}
-size_t wide_steps_smem(int nz, int ny) {
-  const int nyp = (ny + 3) & ~3;
-  return sizeof(double) * (size_t)(5 * nz + 2 * nyp + 320 + 8 + 4);
 }
 
 }  // namespace pmk
@@ -549,8 +698,8 @@ int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, in
   a.it0 = it0;
   a.nsteps = 0;
   const long long K = m->K, it_end = it0 + nsteps;
-  const size_t sm_r = wide_refresh_smem(m->nz, m->ny, m->nb), sm_s = wide_steps_smem(m->nz, m->ny);
-  if (sm_r > 227 * 1024 || sm_s > 227 * 1024) return fail(PMOC_EUNSUPPORTED, "nz too large for shared memory");
+  const size_t sm_r = wide_refresh_smem(m->nz, m->ny, m->nb);
+  if (sm_r > 227 * 1024) return fail(PMOC_EUNSUPPORTED, "nz too large for shared memory");
   if (int rc = launch(k_wide_geo, 64, kWideThreads, 0, stream, a)) return rc;
   if (diagnose_only) return launch(k_wide_refresh, m->M, kWideThreads, sm_r, stream, a);
   long long ii = it0;
@@ -561,7 +710,14 @@ int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, in
     if (stop > it_end) stop = it_end;
     a.it0 = ii;
     a.nsteps = stop - ii;
-    if (int rc = launch(k_wide_steps, m->M, kWideThreads, sm_s, stream, a)) return rc;
+    int rc;
+    if (m->nz <= 4 * kWideCol)
+      rc = launch(k_wide_steps2<4, 2>, m->M, kWideAll, wide_steps2_smem(4, m->ny), stream, a);
+    else if (m->nz <= 8 * kWideCol)
+      rc = launch(k_wide_steps2<8, 3>, m->M, kWideAll, wide_steps2_smem(8, m->ny), stream, a);
+    else
+      rc = launch(k_wide_steps2<16, 4>, m->M, kWideAll, wide_steps2_smem(16, m->ny), stream, a);
+    if (rc) return rc;
     ii = stop;
   }
   return PMOC_OK;
