@@ -43,6 +43,7 @@ WORKLOADS = {
     'C2': (lambda M: configs.c2_column_so(M), 65536, 7200),
     'twocol': (lambda M: configs.twocol(M), 32768, 2400),
     'C3': (lambda M: configs.c3_twocol_so(M), 32768, 2400),
+    'twobasin': (lambda M: configs.twobasin(M), 32768, 2400),
     'C4': (lambda M: configs.c4_jansen_nadeau(M), 32768, 2400),
     'C5': (lambda M: configs.c5_single_global_basin(M), 32768, 2400),
     # BASELINE configs[4]: nz=4096 (block-per-member kernels), stable dt = 0.01 d, K = 72 000
@@ -58,17 +59,30 @@ def algorithmic_flops(spec):
   if spec.north is not None:
     per_step += 11 * n + (2 * n if spec.north.do_conv else 0)
     ncol = 2
+  nclos = 1
+  if getattr(spec, 'pac', None) is not None:  # third column, second thermal wind + remap, second Psi_SO
+    per_step += 11 * n + (2 * n if spec.pac.do_conv else 0)
+    ncol, nclos = 3, 2
   refresh = 3 * n * ncol
   if spec.tw is not None:
-    refresh += 16 * n
+    refresh += nclos * 16 * n
     if spec.iso:
-      refresh += 6 * B * (n - 1) + 8 * n + 2 * B + 2 * n * (math.ceil(math.log2(B)) + 5)
+      refresh += nclos * (6 * B * (n - 1) + 8 * n + 2 * B + 2 * n * (math.ceil(math.log2(B)) + 5))
   if spec.so is not None:
-    refresh += n * (math.ceil(math.log2(spec.so.y.size)) + 20)
+    refresh += nclos * n * (math.ceil(math.log2(spec.so.y.size)) + 20)
   if spec.ml is not None:
     m = spec.ml.y.size
     per_step += m * (math.ceil(math.log2(n)) + 32) + n
   return per_step + refresh / K
+
+
+# DRAM bytes (read + write) of one fused-kernel launch, from the committed `ncu --set full` captures
+# (profiles/r1m_full_summary.txt).  State and parameters are read once and state + diagnostics written once
+# per launch whatever the number of steps, so the 720/240-step captures stand for the bench's launches.
+NCU_TRAFFIC = {  # workload -> (members in the capture, bytes)
+    'C2': (65536, 420.9e6 + 372.2e6),
+    'C3': (32768, 232.3e6 + 375.7e6),
+}
 
 
 # ---------------------------------------------------------------------------- CPU reference
@@ -286,7 +300,10 @@ def gpu_arm(args):
                          % (ens.M * spec.nz * 8 * 3 / 1e6),
                    'parallelism': 'ensemble members sharded over %d GPU(s), no collective in the loop' % world},
         'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
-                     'frac': achieved / peak.value, 'traffic': None,
+                     'frac': achieved / peak.value,
+                     'traffic': (NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
+                                 if args.workload in NCU_TRAFFIC else None),
+                     'traffic_source': 'bytes per launch (dram read + write), profiles/r1m_full_summary.txt',
                      'flops_per_member_step': flops, 'peak_source': 'pmoc_fp64_peak measured live (DFMA stream)',
                      'kernel_ms': ms_per_step},
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,

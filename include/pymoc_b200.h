@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PMOC_ABI_VERSION 1
+#define PMOC_ABI_VERSION 2
 #define PMOC_MAX_NZ_WARP 256 /* one warp per member up to this many levels */
 #define PMOC_MAX_NZ_WIDE 4096 /* one CTA per member up to this many levels ('jn' topology only) */
 #define PMOC_MAX_NY_ML 64    /* SO_ML surface points per member */
@@ -80,6 +80,10 @@ typedef struct {
 #define PMOC_HAS_ML 16u   /* SO_ML mixed layer                                            */
 #define PMOC_SO_BVP 64u   /* set by the library when so_c.ptr != NULL: F2010 smoother of Psi_GM
                              (psi_SO.py:308-323); callers leave it clear */
+#define PMOC_HAS_PAC 128u /* two-basin topology of examples/twobasin_NadeauJansen.py:63-122: a third column
+                             ("Pacific", fields pac / zoc_f / so2_L), a second Psi_Thermwind between basin and pac
+                             (the zonal overturning in the channel) and a second Psi_SO on the pac column.
+                             Needs PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO, order 'post' */
 #define PMOC_ORDER_JN 32u /* loop order + bottom-boundary switches of
                              examples/run_JansenNadeau_2018.py:201-261; otherwise the order of
                              examples/example_twocol_plusSO.py:99-115 */
@@ -94,10 +98,12 @@ typedef struct {
   const double* y; /* [ny] shared channel grid (NULL without SO) */
 
   pmoc_column basin, north;
+  pmoc_column pac; /* PMOC_HAS_PAC only (examples/twobasin_NadeauJansen.py:88) */
 
   /* Psi_Thermwind (psi_thermwind.py:30-70) */
   pmoc_vec tw_f;  /* scalar */
   pmoc_vec tw_b2; /* [nz] fixed northern profile when there is no north column */
+  pmoc_vec zoc_f; /* scalar: f of the basin-pac thermal wind, PMOC_HAS_PAC (twobasin_NadeauJansen.py:69) */
 
   /* Psi_SO (psi_SO.py:17-104) */
   pmoc_vec so_bs;  /* [ny] surface buoyancy (ignored with PMOC_HAS_ML: the mixed layer's bs is used,
@@ -105,6 +111,8 @@ typedef struct {
   pmoc_vec so_tau; /* scalar wind stress, or [ny] when so_tau_on_y != 0 */
   pmoc_vec so_f, so_rho, so_L, so_KGM, so_smax;
   pmoc_vec so_c; /* scalar F2010 phase speed; ptr==NULL -> explicit GM (psi_SO.py:325-327) */
+  pmoc_vec so2_L; /* scalar: zonal length of the pac sector's Psi_SO, which shares every other parameter with
+                     the basin sector's (twobasin_NadeauJansen.py:76-81), PMOC_HAS_PAC */
   int32_t so_tau_on_y;
   int32_t so_bvp_with_Ek;
   /* host-evaluated tapers (psi_SO.py:164-216); all-ones when the height is None, the Ekman
@@ -122,6 +130,10 @@ typedef struct {
   double *psib, *bgrid;                   /* [M, nb]     */
   double *Psi_so, *Psi_Ek, *Psi_GM;       /* [M, nz] Sv */
   double* ml_Psi_s;                       /* [M, ny] Sv */
+  /* PMOC_HAS_PAC: Psi_zon_a / Psi_zon_p / Psi_so2 are carried between launches like Psi_iso_* / Psi_so */
+  double *Psi_zoc, *Psi_zon_a, *Psi_zon_p; /* [M, nz] Sv: ZOC.Psi and its Psibz() legs */
+  double *psib2, *bgrid2;                  /* [M, nb] of the basin-pac remap */
+  double *Psi_so2, *Psi_Ek2, *Psi_GM2;     /* [M, nz] Sv: Psi_SO of the pac sector */
   uint32_t* status;                       /* [M] PMOC_ST_* bits, OR-ed */
 
   /* device scratch, needed only when nz > PMOC_MAX_NZ_WARP: pmoc_model_scratch_bytes(m) bytes.

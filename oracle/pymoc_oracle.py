@@ -438,9 +438,14 @@ def run_coupled(case, nsteps, modes=REFERENCE, it0=0, carry=None):
 
   basin = make_col(case['basin'])
   north = make_col(case['north']) if case.get('north') is not None else None
+  pac = make_col(case['pac']) if case.get('pac') is not None else None  # examples/twobasin_NadeauJansen.py:88
   tw, so, ml = case.get('tw'), case.get('so'), case.get('ml')
   chan = ChannelParams(z, so['y'], so['tau'], **{k: so[k] for k in so if k not in ('y', 'tau', 'bs')}) if so else None
   bs_chan = np.array(so['bs'], dtype=np.float64) if so else None
+  chan_pac = None
+  if pac is not None:  # SO_Pac: same surface buoyancy, wind and eddy parameters, its own zonal length (:80-81)
+    chan_pac = ChannelParams(z, so['y'], so['tau'],
+                             **{**{k: so[k] for k in so if k not in ('y', 'tau', 'bs')}, 'L': case['so_pac_L']})
   layer = MixedLayerState(**ml) if ml else None
   if carry is not None:  # resume (pickup) support: state only, Psi's are re-diagnosed
     basin.b[:] = carry['b_basin']
@@ -448,6 +453,8 @@ def run_coupled(case, nsteps, modes=REFERENCE, it0=0, carry=None):
       north.b[:] = carry['b_north']
     if layer is not None:
       layer.bs[:] = carry['bs_ml']
+    if pac is not None:
+      pac.b[:] = carry['b_pac']
 
   out = {}
 
@@ -458,9 +465,14 @@ def run_coupled(case, nsteps, modes=REFERENCE, it0=0, carry=None):
       if case.get('iso', False):
         out['Psi_iso_b'], out['Psi_iso_n'], out['psib'], out['bgrid'] = thermwind_psibz(
             out['Psi_tw'], basin.b, b2, nb)
+    if pac is not None:  # ZOC between the two basins (:117-119)
+      out['Psi_zoc'] = thermwind_solve(z, basin.b, pac.b, case['zoc_f'], modes.thermwind)
+      out['Psi_zon_a'], out['Psi_zon_p'], out['psib2'], out['bgrid2'] = thermwind_psibz(out['Psi_zoc'], basin.b, pac.b, nb)
     if so:
       surf = layer.bs if layer is not None else bs_chan
       out['Psi_so'], out['Psi_Ek'], out['Psi_GM'] = so_solve(chan, basin.b, surf, modes.ys)
+      if pac is not None:
+        out['Psi_so2'], out['Psi_Ek2'], out['Psi_GM2'] = so_solve(chan_pac, pac.b, surf, modes.ys)
 
   def velocities():
     north_leg = (out['Psi_iso_b'] if case.get('iso', False) else out['Psi_tw']) if tw else 0. * z
@@ -476,9 +488,14 @@ def run_coupled(case, nsteps, modes=REFERENCE, it0=0, carry=None):
       out.update(carry['psi'])
     for ii in range(it0, it0 + nsteps):
       wAb, wAn = velocities()
+      if pac is not None:  # examples/twobasin_NadeauJansen.py:104-109
+        wAb = (out['Psi_iso_b'] + out['Psi_zon_a'] - out['Psi_so']) * 1e6
+        wAp = (-out['Psi_zon_p'] - out['Psi_so2']) * 1e6
       column_timestep(basin, wAb, dt, basin.do_conv)
       if north is not None:
         column_timestep(north, wAn, dt, north.do_conv)
+      if pac is not None:
+        column_timestep(pac, wAp, dt, pac.do_conv)
       if ii % K == 0:
         refresh()
   else:
@@ -510,6 +527,8 @@ def run_coupled(case, nsteps, modes=REFERENCE, it0=0, carry=None):
   out['b_basin'] = basin.b.copy()
   if north is not None:
     out['b_north'] = north.b.copy()
+  if pac is not None:
+    out['b_pac'] = pac.b.copy()
   if layer is not None:
     out['bs_ml'] = layer.bs.copy()
     out['Psi_s'] = None if layer.Psi_s is None else layer.Psi_s.copy()

@@ -1,7 +1,9 @@
 #!/usr/bin/env python
 """Attribute an ncu source-page CSV (SASS view) to source lines with nvdisasm's line table.
 
-    python profiles/lines.py <prof.source.csv[.gz]> <object.o> <kernel-substr> [top]
+    python profiles/lines.py <prof.source.csv[.gz]> <object.o> <kernel-substr> [top] [source-dir]
+
+(the object must be the build that was profiled: `unmatched` counts opcode disagreements)
 
 The SASS page of `ncu --page source --csv` carries per-instruction counters but no line numbers;
 `nvdisasm -g` of the same build carries the line of every instruction offset.  Joined on the
@@ -50,6 +52,7 @@ def functions(path):
 def main():
   src, obj, kernel = sys.argv[1:4]
   top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+  srcdir = sys.argv[5] if len(sys.argv) > 5 else None
   op = gzip.open if src.endswith('.gz') else open
   rows = list(csv.reader(io.StringIO(op(src, 'rt').read())))
   h = next(i for i, r in enumerate(rows) if r and r[0] == 'Address')
@@ -71,7 +74,7 @@ def main():
     tot += n
     tots += s
   print('%d SASS instructions, %d unmatched; %d warp-instructions executed, %d stall samples' % (len(rows), bad, tot, tots))
-  root = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'pymoc_b200', 'csrc')
+  root = srcdir or os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'pymoc_b200', 'csrc')
   buckets, buckets_s = defaultdict(int), defaultdict(int)
   fcache = {}
   for (f, l), n in per_line.items():
@@ -93,4 +96,7 @@ def main():
 
 
 if __name__ == '__main__':
-  main()
+  try:
+    main()
+  except BrokenPipeError:
+    pass

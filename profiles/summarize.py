@@ -3,6 +3,7 @@
 
     python profiles/summarize.py launches <launch-list.csv>          # --metrics gpu__time_duration.sum pass
     python profiles/summarize.py full <report.ncu-rep> [kernel-substr]   # --set full capture
+    python profiles/summarize.py raw <raw-page.csv> [kernel-substr]      # `ncu -i rep --page raw --csv` of such a capture
 
 The launch list gives each kernel's share of the profiled command; the full capture gives
 the counters quoted in DESIGN.md / bench.py (FP64 pipe utilisation, DRAM bytes, occupancy,
@@ -45,8 +46,9 @@ def launches(path):
     print('%-92s %6d %12.1f %6.1f%%' % (name, n, t / 1e3, 100 * t / total))
 
 
-def full(path, substr=''):
-  out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+def full(path, substr='', is_csv=False):
+  out = open(path).read() if is_csv else subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'],
+                                                          capture_output=True, text=True).stdout
   rows = list(csv.reader(io.StringIO(out)))
   hdr, units, rows = rows[0], rows[1], rows[2:]
   for r in rows:
@@ -68,4 +70,4 @@ if __name__ == '__main__':
   if sys.argv[1] == 'launches':
     launches(sys.argv[2])
   else:
-    full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else '')
+    full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else '', is_csv=sys.argv[1] == 'raw')

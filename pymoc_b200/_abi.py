@@ -1,12 +1,12 @@
 """ctypes mirror of ``include/pymoc_b200.h`` (keep the two in sync; ABI version checked at load)."""
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE = range(5)
 STATUS_NAMES = {1: 'EINVAL', 2: 'EUNSUPPORTED', 3: 'ECUDA', 4: 'ENODEVICE'}
 
-HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP = 1, 2, 4, 8, 16, 32, 64
+HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP, HAS_PAC = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_CONVECT, STAGE_VERTADVDIFF, STAGE_HORADV = 1, 2, 4
 ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES, ST_NOISE_SWITCH = 1, 2, 4, 8, 16, 32, 64
 
@@ -26,17 +26,20 @@ class Model(C.Structure):
   _fields_ = [
       ('M', C.c_int64), ('nz', C.c_int32), ('ny', C.c_int32), ('nb', C.c_int32), ('K', C.c_int32),
       ('flags', C.c_uint32), ('dt', C.c_double), ('z', C.c_void_p), ('y', C.c_void_p),
-      ('basin', Column), ('north', Column),
-      ('tw_f', Vec), ('tw_b2', Vec),
+      ('basin', Column), ('north', Column), ('pac', Column),
+      ('tw_f', Vec), ('tw_b2', Vec), ('zoc_f', Vec),
       ('so_bs', Vec), ('so_tau', Vec), ('so_f', Vec), ('so_rho', Vec), ('so_L', Vec), ('so_KGM', Vec),
-      ('so_smax', Vec), ('so_c', Vec), ('so_tau_on_y', C.c_int32), ('so_bvp_with_Ek', C.c_int32),
+      ('so_smax', Vec), ('so_c', Vec), ('so2_L', Vec), ('so_tau_on_y', C.c_int32), ('so_bvp_with_Ek', C.c_int32),
       ('so_sill_taper', C.c_void_p), ('so_ek_taper', C.c_void_p), ('so_top_taper', C.c_void_p),
       ('so_bot_taper', C.c_void_p),
       ('ml_bs', C.c_void_p), ('ml_Ks', Vec), ('ml_h', Vec), ('ml_L', Vec), ('ml_vpist', Vec),
       ('ml_surflux', Vec), ('ml_rest_mask', Vec), ('ml_b_rest', Vec),
       ('Psi_tw', C.c_void_p), ('Psi_iso_b', C.c_void_p), ('Psi_iso_n', C.c_void_p), ('psib', C.c_void_p),
       ('bgrid', C.c_void_p), ('Psi_so', C.c_void_p), ('Psi_Ek', C.c_void_p), ('Psi_GM', C.c_void_p),
-      ('ml_Psi_s', C.c_void_p), ('status', C.c_void_p), ('scratch', C.c_void_p), ('scratch_bytes', C.c_uint64),
+      ('ml_Psi_s', C.c_void_p),
+      ('Psi_zoc', C.c_void_p), ('Psi_zon_a', C.c_void_p), ('Psi_zon_p', C.c_void_p), ('psib2', C.c_void_p),
+      ('bgrid2', C.c_void_p), ('Psi_so2', C.c_void_p), ('Psi_Ek2', C.c_void_p), ('Psi_GM2', C.c_void_p),
+      ('status', C.c_void_p), ('scratch', C.c_void_p), ('scratch_bytes', C.c_uint64),
   ]
 
 

@@ -135,6 +135,50 @@ def c3_twocol_so(M=262144, c=None, axes=None):
       order='post', iso=True)
 
 
+# ------------------------------------------------------------------------ two basins
+def twobasin(M=1, axes=None):
+  """examples/twobasin_NadeauJansen.py:22-122 -- Atlantic + northern sinking region + Pacific,
+  AMOC and zonal (inter-basin) thermal-wind overturning with isopycnal mapping, one Psi_SO per
+  basin sector.  Lattice: tau x KGM x bs_north.
+
+  The script diagnoses its pre-loop AMOC against ``0.01*b_Atl`` instead of the northern column
+  (:63); that streamfunction is used for iteration 0 only.  Here, as in every other topology, the
+  pre-loop diagnosis uses the column states.
+  """
+  bs, bAABW = 0.02, -0.0011
+  y = np.asarray(np.linspace(0, 3.e6, 51))
+  offset = 0.0345 * (1 - np.cos(np.pi * (5.55e5 - 1.e5) / 8e6))
+  bs_SO = (0.0345 * (1 - np.cos(np.pi * (y - 1.e5) / 8e6)) * (y > 5.55e5)
+           + (bAABW - offset) / 5.55e5 * np.maximum(0, 5.55e5 - y) + offset * (y < 5.55e5))
+  dt = 86400. * 30.
+  K = int(np.floor(2. * 360 * 86400 / dt))
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  kappa = 1.0 * (1e-4 * (1.1 - np.tanh(np.maximum(z + 2000., 0) / 1000. + np.minimum(z + 2000., 0) / 1300.))
+                 * (1. - np.maximum(-4000. - z + 600., 0.) / 600.)**2)
+  if M == 1:
+    sweep = lattice(tau=[0.16], KGM=[1800.], bs_north=[0.00036])
+  else:
+    n = axes if axes is not None else _sizes(M, 3)
+    sweep = lattice(tau=np.linspace(0.1, 0.2, n[0]) if n[0] > 1 else [0.16],
+                    KGM=np.linspace(1400., 2200., n[1]) if n[1] > 1 else [1800.],
+                    bs_north=np.linspace(0.0002, 0.0006, n[2]) if n[2] > 1 else [0.00036])
+  assert sweep['tau'].size == M
+  bs_north = sweep['bs_north']
+  bbot = np.minimum(bAABW, bs_north)
+  A_Atl, A_north, A_Pac = 7e13, 5.5e12, 1.7e14
+  Lx = 1.3e+07
+  Latl, Lpac = 6. / 21. * Lx, 15. / 21. * Lx
+  b0 = bs * np.exp(z / 300.)[None, :] + (z / z[0])[None, :] * bbot[:, None]
+  return ModelSpec(
+      M=M, z=z, dt=dt, K=K, nb=500, name='twobasin_NadeauJansen', sweep=sweep,
+      basin=ColumnSpec.build(z, kappa, A_Atl, bs, b0, bbot=bbot, N2min=2e-7),
+      north=ColumnSpec.build(z, kappa, A_north, bs_north, b0, bbot=bbot, N2min=2e-7, do_conv=True),
+      pac=ColumnSpec.build(z, kappa, A_Pac, bs, b0, bbot=bbot, N2min=2e-7),
+      tw=ThermwindSpec.build(z, f=1.2e-4), zoc_f=1e-4, so_pac_L=Lpac,
+      so=ChannelSpec.build(y, bs_SO, sweep['tau'], L=Latl, KGM=sweep['KGM']),
+      order='post', iso=True)
+
+
 # ------------------------------------------------------------------------ C4 / C5
 _KAPGCM = np.array([
     1.2e-4, 0.882e-4, 0.544e-4, 0.393e-4, 0.305e-4, 0.235e-4, 0.207e-4, 0.210e-4, 0.213e-4, 0.216e-4,

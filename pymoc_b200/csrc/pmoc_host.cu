@@ -99,6 +99,19 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
   d.y = mr.in(m->y, ny);
   d.basin = mirror_column(mr, m->basin, M, nz);
   if (f & PMOC_HAS_NORTH) d.north = mirror_column(mr, m->north, M, nz);
+  if (f & PMOC_HAS_PAC) {
+    d.pac = mirror_column(mr, m->pac, M, nz);
+    d.zoc_f = mr.in(m->zoc_f, M, 1);
+    d.so2_L = mr.in(m->so2_L, M, 1);
+    d.Psi_zoc = mr.out(m->Psi_zoc, (size_t)M * nz, carry);
+    d.Psi_zon_a = mr.out(m->Psi_zon_a, (size_t)M * nz, carry);
+    d.Psi_zon_p = mr.out(m->Psi_zon_p, (size_t)M * nz, carry);
+    d.psib2 = mr.out(m->psib2, (size_t)M * nb, carry);
+    d.bgrid2 = mr.out(m->bgrid2, (size_t)M * nb, carry);
+    d.Psi_so2 = mr.out(m->Psi_so2, (size_t)M * nz, carry);
+    d.Psi_Ek2 = mr.out(m->Psi_Ek2, (size_t)M * nz, carry);
+    d.Psi_GM2 = mr.out(m->Psi_GM2, (size_t)M * nz, carry);
+  }
   d.tw_f = mr.in(m->tw_f, M, 1);
   d.tw_b2 = mr.in(m->tw_b2, M, nz);
   d.so_bs = mr.in(m->so_bs, M, ny);

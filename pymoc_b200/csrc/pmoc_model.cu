@@ -13,6 +13,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
   constexpr bool BVP = (TOPO & PMOC_SO_BVP) != 0;  // F2010 smoother of Psi_GM
+  constexpr bool PAC = (TOPO & PMOC_HAS_PAC) != 0;  // third column + zonal thermal wind + second Psi_SO
   const pmoc_model& M = a.m;
   const SmemPlan& sp = a.sp;
   const int nz = M.nz, ny = M.ny, nb = M.nb;
@@ -37,17 +38,22 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   if (m >= M.M) return;
   const double dt = M.dt;
 
-  ColRegs<LPL> cb, cn;
+  ColRegs<LPL> cb, cn, cp;
   pm::ExactGeo EG{};
   pm::ExactCol xb{}, xn{};
   col_load<LPL>(cb, M.basin, m, nz);
   if (NORTH) col_load<LPL>(cn, M.north, m, nz);
+  if (PAC) col_load<LPL>(cp, M.pac, m, nz);
   if (!ML) {
     cb.tab = coltab_of(ws, sp, 0);
     col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
     if (NORTH) {
       cn.tab = coltab_of(ws, sp, 1);
       col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
+    }
+    if (PAC) {
+      cp.tab = coltab_of(ws, sp, 2);
+      col_retabulate<LPL>(cp, M.pac, m, G, nz, dt);
     }
   } else {
     EG = exactgeo_of(sm, sp);
@@ -61,6 +67,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   double b2fix[LPL];
   if (TW && !NORTH) pm::load_lev<LPL>(b2fix, vrow(M.tw_b2, m), nz, 0.0);
   const double tw_f = TW ? vat(M.tw_f, m) : 1.0;
+  const double zoc_f = PAC ? vat(M.zoc_f, m) : 1.0;
   pm::SoPar so{};
   pm::SoSurf surf{};
   if (SO) {
@@ -84,6 +91,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     rt::syncwarp();
     if (!ML) surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);  // bs(y) is fixed without a mixed layer
   }
+  pm::SoPar so2 = so;  // the pac sector's Psi_SO differs in its zonal length only (twobasin_NadeauJansen.py:76-81)
+  if (PAC) so2.L = vat(M.so2_L, m);
   unsigned status = 0;
   pm::MlState ml{};
   double* const bb_s = ws + (ML ? sp.w_bb : 0);
@@ -97,10 +106,19 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   }
 
   // Streamfunctions -> stencil coefficients of the columns (and what SO_ML needs).
-  auto apply = [&](const double(&north_leg)[LPL], const double(&iso_n)[LPL], const double(&psi_so)[LPL]) {
+  auto apply = [&](const double(&north_leg)[LPL], const double(&iso_n)[LPL], const double(&psi_so)[LPL],
+                   const double(&zon_a)[LPL], const double(&zon_p)[LPL], const double(&psi_so2)[LPL]) {
     double wA[LPL];
-    PM_UNROLL
-    for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? north_leg[j] : 0.0) - (SO ? psi_so[j] : 0.0)) * 1e6;
+    if (PAC) {  // twobasin_NadeauJansen.py:104-106
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = (-zon_p[j] - psi_so2[j]) * 1e6;
+      pm::col_coeffs<LPL>(cp.p, cp.q, wA, cp.tab, G, nz);
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = (north_leg[j] + zon_a[j] - psi_so[j]) * 1e6;
+    } else {
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) wA[j] = ((TW ? north_leg[j] : 0.0) - (SO ? psi_so[j] : 0.0)) * 1e6;
+    }
     if (ML)
       pm::col_nweff<LPL>(xb, wA, vrow(M.basin.dAk, m), nz, M.basin.nvar);
     else
@@ -134,9 +152,9 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
 
   // Diagnose the streamfunctions from the current state and fold them into the stencils.
   auto refresh = [&](bool write) {
-    double psi_tw[LPL], iso_b[LPL], iso_n[LPL], psi_so[LPL];
+    double psi_tw[LPL], iso_b[LPL], iso_n[LPL], psi_so[LPL], zon_a[LPL], zon_p[LPL], psi_so2[LPL];
     PM_UNROLL
-    for (int j = 0; j < LPL; ++j) psi_tw[j] = iso_b[j] = iso_n[j] = psi_so[j] = 0.0;
+    for (int j = 0; j < LPL; ++j) psi_tw[j] = iso_b[j] = iso_n[j] = psi_so[j] = zon_a[j] = zon_p[j] = psi_so2[j] = 0.0;
     if (TW) {
       const double(&b2)[LPL] = NORTH ? cn.b : b2fix;
       pm::tw_solve<LPL>(psi_tw, cb.b, b2, tw_f, zs, nz, nullptr);
@@ -162,6 +180,29 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         rt::syncwarp();
       }
     }
+    if (PAC) {  // ZOC.update(b1=Atl.b, b2=Pac.b); ZOC.solve(); ZOC.Psibz()  (twobasin_NadeauJansen.py:117-119)
+      double psi_zoc[LPL];
+      pm::tw_solve<LPL>(psi_zoc, cb.b, cp.b, zoc_f, zs, nz, nullptr);
+      if (write && M.Psi_zoc) pm::store_lev<LPL>(psi_zoc, M.Psi_zoc + m * nz, nz);
+      double* psib_s = ws + sp.w_psib;
+      const pm::BGrid BG = pm::tw_psib<LPL>(psi_zoc, cb.b, cp.b, nz, nb, ws + sp.w_remap, psib_s,
+                                            reinterpret_cast<int*>(ws + sp.w_cnt));
+      PM_UNROLL
+      for (int j = 0; j < LPL; ++j) {
+        const bool ok = pm::lev<LPL>(j) < nz;
+        zon_a[j] = ok ? pm::interp_bgrid(cb.b[j], BG, psib_s) : 0.0;
+        zon_p[j] = ok ? pm::interp_bgrid(cp.b[j], BG, psib_s) : 0.0;
+      }
+      if (write) {
+        pm::store_lev<LPL>(zon_a, M.Psi_zon_a + m * nz, nz);
+        pm::store_lev<LPL>(zon_p, M.Psi_zon_p + m * nz, nz);
+        if (M.psib2)
+          for (int i = L; i < nb; i += 32) M.psib2[m * nb + i] = psib_s[i];
+        if (M.bgrid2)
+          for (int i = L; i < nb; i += 32) M.bgrid2[m * nb + i] = BG.at(i);
+      }
+      rt::syncwarp();
+    }
     if (SO) {
       double ek[LPL], gm[LPL], ysv[LPL];
       if (ML) {  // the channel's surface buoyancy is the mixed layer's (run_JansenNadeau_2018.py:214)
@@ -178,11 +219,20 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
         if (M.Psi_Ek) pm::store_lev<LPL>(ek, M.Psi_Ek + m * nz, nz);
         if (M.Psi_GM) pm::store_lev<LPL>(gm, M.Psi_GM + m * nz, nz);
       }
+      if (PAC) {  // SO_Pac.update(b=Pac.b); SO_Pac.solve()  (twobasin_NadeauJansen.py:122-123)
+        pm::so_solve<LPL, false>(psi_so2, ek, gm, ysv, cp.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so2, zs, nz,
+                                 &status);
+        if (write) {
+          pm::store_lev<LPL>(psi_so2, M.Psi_so2 + m * nz, nz);
+          if (M.Psi_Ek2) pm::store_lev<LPL>(ek, M.Psi_Ek2 + m * nz, nz);
+          if (M.Psi_GM2) pm::store_lev<LPL>(gm, M.Psi_GM2 + m * nz, nz);
+        }
+      }
     }
     if (ISO)
-      apply(iso_b, iso_n, psi_so);
+      apply(iso_b, iso_n, psi_so, zon_a, zon_p, psi_so2);
     else
-      apply(psi_tw, iso_n, psi_so);
+      apply(psi_tw, iso_n, psi_so, zon_a, zon_p, psi_so2);
     if (ML) {  // the remap scratch overlaid the column tables (plan_smem)
       pm::col_tabulate_exact<LPL>(xb, vrow(M.basin.kappa, m), vrow(M.basin.Area, m), nz, M.basin.nvar);
       pm::col_tabulate_exact<LPL>(xn, vrow(M.north.kappa, m), vrow(M.north.Area, m), nz, M.north.nvar);
@@ -194,13 +244,18 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
   // the 'jn' order diagnoses at the top of iteration it % K == 0 and then needs nothing carried
   const bool dg = a.diagnose_only != 0;
   if (!dg && (!ML || a.it0 % K != 0)) {
-    double t1[LPL], t2[LPL], t3[LPL];
+    double t1[LPL], t2[LPL], t3[LPL], t4[LPL], t5[LPL], t6[LPL];
     PM_UNROLL
-    for (int j = 0; j < LPL; ++j) t1[j] = t2[j] = t3[j] = 0.0;
+    for (int j = 0; j < LPL; ++j) t1[j] = t2[j] = t3[j] = t4[j] = t5[j] = t6[j] = 0.0;
     if (TW) pm::load_lev<LPL>(t1, (ISO ? M.Psi_iso_b : M.Psi_tw) + m * nz, nz, 0.0);
     if (NORTH) pm::load_lev<LPL>(t2, M.Psi_iso_n + m * nz, nz, 0.0);
     if (SO) pm::load_lev<LPL>(t3, M.Psi_so + m * nz, nz, 0.0);
-    apply(t1, t2, t3);
+    if (PAC) {
+      pm::load_lev<LPL>(t4, M.Psi_zon_a + m * nz, nz, 0.0);
+      pm::load_lev<LPL>(t5, M.Psi_zon_p + m * nz, nz, 0.0);
+      pm::load_lev<LPL>(t6, M.Psi_so2 + m * nz, nz, 0.0);
+    }
+    apply(t1, t2, t3, t4, t5, t6);
   }
 
   if (!ML && !dg) {
@@ -211,6 +266,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
     if (NORTH) {
       if (!cn.conv) pm::set_level<LPL>(cn.b, nz - 1, cn.bs);
       if (cn.plain) col_bottom<LPL>(cn, zs);
+    }
+    if (PAC) {
+      if (!cp.conv) pm::set_level<LPL>(cp.b, nz - 1, cp.bs);
+      if (cp.plain) col_bottom<LPL>(cp, zs);
     }
   }
   // One loop for both orders, with a single (inlined) copy of the diagnosis:
@@ -236,6 +295,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
       for (int s = 0; s < n; ++s) {
         col_advance<LPL>(cb, G, nz);
         if (NORTH) col_advance<LPL>(cn, G, nz);
+        if (PAC) col_advance<LPL>(cp, G, nz);
       }
       ii += n;
       refresh_next = hits;
@@ -302,12 +362,14 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
 
   pm::store_lev<LPL>(cb.b, M.basin.b + m * nz, nz);
   if (NORTH) pm::store_lev<LPL>(cn.b, M.north.b + m * nz, nz);
+  if (PAC) pm::store_lev<LPL>(cp.b, M.pac.b + m * nz, nz);
   bool bad = false;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     if (pm::lev<LPL>(j) < nz) {
       bad |= !(fabs(cb.b[j]) <= 1.79e308);
       if (NORTH) bad |= !(fabs(cn.b[j]) <= 1.79e308);
+      if (PAC) bad |= !(fabs(cp.b[j]) <= 1.79e308);
     }
   }
   if (ML) {
@@ -321,7 +383,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
 
 template <int LPL>
 int launch_model(const RunArgs& ra, void* stream) {
-  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP);
+  const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP | PMOC_HAS_PAC);
   const long long grid = blocks_for(ra.m.M);
   const int block = 32 * kWarpsPerBlock;
   const size_t smem = ra.sp.bytes(kWarpsPerBlock);
@@ -336,6 +398,7 @@ int launch_model(const RunArgs& ra, void* stream) {
     PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO)
     PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO)
     PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_SO_BVP)
+    PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_PAC)
     PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML)
     PM_CASE(PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP)
     default: return fail(PMOC_EUNSUPPORTED, "module combination has no fused kernel");

@@ -255,6 +255,16 @@ int check_model(const pmoc_model* m) {
       return fail(PMOC_EINVAL, "Psi_SO parameters incomplete");
     if (!(f & PMOC_HAS_ML) && !m->so_bs.ptr) return fail(PMOC_EINVAL, "so_bs missing");
   }
+  if (f & PMOC_HAS_PAC) {
+    const unsigned need = PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO;
+    if ((f & need) != need || (f & (PMOC_HAS_ML | PMOC_ORDER_JN)))
+      return fail(PMOC_EINVAL, "the two-basin topology needs basin + north + thermal wind (iso) + Psi_SO, order 'post'");
+    if (check_column(m->pac, "pac column incomplete")) return PMOC_EINVAL;
+    if (!m->zoc_f.ptr || !m->so2_L.ptr || !m->Psi_zon_a || !m->Psi_zon_p || !m->Psi_so2)
+      return fail(PMOC_EINVAL, "zoc_f / so2_L / Psi_zon_a / Psi_zon_p / Psi_so2 missing");
+    if (m->so_c.ptr) return fail(PMOC_EUNSUPPORTED, "the two-basin topology has no F2010 smoother kernel");
+    if (m->nz > PMOC_MAX_NZ_WARP) return fail(PMOC_EUNSUPPORTED, "the two-basin topology needs nz <= 256");
+  }
   if (((f & PMOC_HAS_ML) != 0) != ((f & PMOC_ORDER_JN) != 0))
     return fail(PMOC_EUNSUPPORTED, "SO_ML is stepped by the 'jn' loop order only (and that order needs SO_ML)");
   if (f & PMOC_HAS_ML) {

@@ -55,6 +55,8 @@ def topology_flags(spec: ModelSpec) -> int:
     f |= _abi.HAS_ML
   if spec.order == 'jn':
     f |= _abi.ORDER_JN
+  if spec.pac is not None:
+    f |= _abi.HAS_PAC
   return f
 
 
@@ -174,6 +176,15 @@ class Ensemble:
       m.Psi_so = self._out((M, nz), 'Psi_so')
       m.Psi_Ek = self._out((M, nz), 'Psi_Ek')
       m.Psi_GM = self._out((M, nz), 'Psi_GM')
+    if s.pac is not None:
+      m.pac = self._column(s.pac, 'pac')
+      m.zoc_f = self._vec(s.zoc_f)
+      m.so2_L = self._vec(s.so_pac_L)
+      for attr, name, shape in (('Psi_zoc', 'Psi_zoc', (M, nz)), ('Psi_zon_a', 'Psi_zon_a', (M, nz)),
+                                ('Psi_zon_p', 'Psi_zon_p', (M, nz)), ('psib2', 'psib2', (M, s.nb)),
+                                ('bgrid2', 'bgrid2', (M, s.nb)), ('Psi_so2', 'Psi_so2', (M, nz)),
+                                ('Psi_Ek2', 'Psi_Ek2', (M, nz)), ('Psi_GM2', 'Psi_GM2', (M, nz))):
+        setattr(m, attr, self._out(shape, name))
     if s.ml is not None:
       ml = s.ml
       m.ml_bs = self._state(ml.bs0, 'bs_ml')
@@ -209,13 +220,14 @@ class Ensemble:
     """Prognostic arrays as numpy: b_basin[, b_north][, bs_ml] -- exactly what the reference's
     pickup files hold (examples/run_JansenNadeau_2018.py:266-267)."""
     self.be.sync()
-    keys = [k for k in ('b_basin', 'b_north', 'bs_ml') if k in self._bufs]
+    keys = [k for k in ('b_basin', 'b_north', 'b_pac', 'bs_ml') if k in self._bufs]
     return {k: self.be.download(self._bufs[k]) for k in keys}
 
   def diagnostics(self):
     self.be.sync()
     keys = [k for k in ('Psi_tw', 'Psi_iso_b', 'Psi_iso_n', 'psib', 'bgrid', 'Psi_so', 'Psi_Ek', 'Psi_GM', 'Psi_s',
-                        'status', 'bbot_basin', 'bbot_north', 'var_basin', 'var_north') if k in self._bufs]
+                        'status', 'bbot_basin', 'bbot_north', 'var_basin', 'var_north', 'Psi_zoc', 'Psi_zon_a',
+                        'Psi_zon_p', 'psib2', 'bgrid2', 'Psi_so2', 'Psi_Ek2', 'Psi_GM2') if k in self._bufs]
     out = {k: self.be.download(self._bufs[k]) for k in keys}
     out['status'] = out['status'].view(np.uint32)
     return out

@@ -160,6 +160,10 @@ class ModelSpec:
                 run_single_global_basin.py:172-229).
   iso         : columns are forced with the isopycnally remapped streamfunction
                 (``Psibz``) instead of the z-space one.
+  pac         : the two-basin topology of examples/twobasin_NadeauJansen.py:63-122 -- a third
+                column coupled to ``basin`` through a second thermal-wind closure (``zoc_f``,
+                the zonal overturning in the channel) and to the channel through a second
+                ``Psi_SO`` that differs from ``so`` in its zonal length ``so_pac_L`` only.
   """
   M: int
   z: np.ndarray
@@ -170,6 +174,9 @@ class ModelSpec:
   tw: Optional[ThermwindSpec] = None
   so: Optional[ChannelSpec] = None
   ml: Optional[MixedLayerSpec] = None
+  pac: Optional[ColumnSpec] = None
+  zoc_f: Optional[np.ndarray] = None  # [1|M]
+  so_pac_L: Optional[np.ndarray] = None  # [1|M]
   order: str = 'post'
   iso: bool = False
   nb: int = 500
@@ -188,6 +195,12 @@ class ModelSpec:
       raise ValueError('a north column is coupled through the isopycnal thermal-wind closure')
     if self.tw is not None and self.north is None and self.tw.b2 is None:
       raise ValueError('tw.b2 is needed when there is no north column')
+    if self.pac is not None:
+      if not (self.north and self.tw and self.iso and self.so) or self.ml is not None or self.order != 'post':
+        raise ValueError("the two-basin topology needs basin + north + tw (iso) + so, order 'post', no mixed layer")
+      if self.zoc_f is None or self.so_pac_L is None:
+        raise ValueError('pac needs zoc_f and so_pac_L')
+      self.zoc_f, self.so_pac_L = _vec(self.zoc_f, 'zoc_f'), _vec(self.so_pac_L, 'so_pac_L')
 
   @property
   def nz(self):
@@ -210,6 +223,10 @@ class ModelSpec:
     case = dict(z=self.z.copy(), dt=float(self.dt), K=int(self.K), nb=int(self.nb), order=self.order,
                 iso=bool(self.iso), basin=col(self.basin),
                 north=None if self.north is None else col(self.north), tw=None, so=None, ml=None)
+    if self.pac is not None:
+      case['pac'] = col(self.pac)
+      case['zoc_f'] = float(pick(self.zoc_f))
+      case['so_pac_L'] = float(pick(self.so_pac_L))
     if self.tw is not None:
       case['tw'] = dict(f=float(pick(self.tw.f)), b2=None if self.tw.b2 is None else pick(self.tw.b2).copy())
     if self.so is not None:

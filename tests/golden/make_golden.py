@@ -63,8 +63,10 @@ def run_reference(case, checkpoints):
   z, dt, K, nb = case['z'], case['dt'], case['K'], case['nb']
   basin = _column(z, case['basin'])
   north = _column(z, case['north']) if case['north'] is not None else None
+  pac = _column(z, case['pac']) if case.get('pac') is not None else None
   tw, so, ml = case['tw'], case['so'], case['ml']
   snaps = {}
+  two = {}  # the second closure pair of the two-basin topology
 
   def snapshot(n, AMOC, SO, iso, channel):
     s = dict(b_basin=basin.b.copy())
@@ -80,6 +82,12 @@ def run_reference(case, checkpoints):
     if channel is not None:
       s['bs_ml'] = channel.bs.copy()
       s['Psi_s'] = channel.Psi_s.copy()
+    if pac is not None:
+      s['b_pac'] = pac.b.copy()
+      s['Psi_zoc'] = two['ZOC'].Psi.copy()
+      s['Psi_zon_a'], s['Psi_zon_p'] = two['zon'][0].copy(), two['zon'][1].copy()
+      s['bgrid2'] = two['ZOC'].bgrid.copy()
+      s['Psi_so2'], s['Psi_Ek2'], s['Psi_GM2'] = two['SO'].Psi.copy(), two['SO'].Psi_Ek.copy(), two['SO'].Psi_GM.copy()
     snaps[str(n)] = s
 
   if case['order'] == 'post':
@@ -94,14 +102,31 @@ def run_reference(case, checkpoints):
     if so is not None:
       SO = _channel(z, so, basin.b.copy())
       SO.solve()
+    if pac is not None:  # examples/twobasin_NadeauJansen.py:68-81
+      two['ZOC'] = Psi_Thermwind(z=z, b1=basin.b, b2=pac.b, f=case['zoc_f'])
+      two['ZOC'].solve()
+      two['zon'] = two['ZOC'].Psibz(nb)
+      two['SO'] = _channel(z, {**so, 'L': case['so_pac_L']}, pac.b.copy())
+      two['SO'].solve()
     for ii in range(max(checkpoints)):
       north_leg = (iso[0] if case['iso'] else AMOC.Psi) if AMOC is not None else 0. * z
       south_leg = SO.Psi if SO is not None else 0. * z
       wAb = (north_leg - south_leg) * 1e6
+      if pac is not None:  # :104-109
+        wAb = (iso[0] + two['zon'][0] - SO.Psi) * 1e6
+        wA_Pac = (-two['zon'][1] - two['SO'].Psi) * 1e6
       basin.timestep(wA=wAb, dt=dt, do_conv=case['basin']['do_conv'])
       if north is not None:
         wAN = -iso[1] * 1e6
         north.timestep(wA=wAN, dt=dt, do_conv=case['north']['do_conv'])
+      if pac is not None:
+        pac.timestep(wA=wA_Pac, dt=dt, do_conv=case['pac']['do_conv'])
+        if ii % K == 0:  # :117-123 (after the AMOC update below in the script; the two are independent)
+          two['ZOC'].update(b1=basin.b, b2=pac.b)
+          two['ZOC'].solve()
+          two['zon'] = two['ZOC'].Psibz(nb)
+          two['SO'].update(b=pac.b)
+          two['SO'].solve()
       if ii % K == 0:
         if AMOC is not None:
           if north is not None:
@@ -365,6 +390,8 @@ if __name__ == '__main__':
     coupled_fixture('c4.npz', configs.c4_jansen_nadeau(32, axes=(2, 2, 2, 2, 2)), [0, 13, 22, 31], [1, 12, 13, 600, 2400])
   if want('c4_literal'):
     coupled_fixture('c4_literal.npz', configs.c4_jansen_nadeau(1), [0], [1, 120, 1200])
+  if want('twobasin'):
+    coupled_fixture('twobasin.npz', configs.twobasin(8, axes=(2, 2, 2)), [0, 5, 7], [1, 25, 480, 1200])
   if want('c5'):
     coupled_fixture('c5.npz', configs.c5_single_global_basin(1), [0], [1, 24, 25, 480])
   # columns taller than one warp holds (block-per-member kernels): nz=320 over two refreshes, and the

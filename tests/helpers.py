@@ -49,7 +49,8 @@ def spec_from_cases(cases):
     return cs
 
   basin, north = col('basin'), col('north')
-  for cs, name in ((basin, 'basin'), (north, 'north')):
+  pac = col('pac') if c0.get('pac') is not None else None
+  for cs, name in ((basin, 'basin'), (north, 'north'), (pac, 'pac')):
     if cs is not None:
       cs.kappa = np.ascontiguousarray(stack(lambda c: c[name]['kappa']))  # [M, nvar, nz]
   tw = so = ml = None
@@ -68,4 +69,6 @@ def spec_from_cases(cases):
     ml = MixedLayerSpec.build(c0['ml']['y'], g('bs'), Ks=g('Ks'), h=g('h'), L=g('L'), surflux=g('surflux'),
                               rest_mask=g('rest_mask'), b_rest=g('b_rest'), v_pist=g('v_pist'))
   return ModelSpec(M=len(cases), z=z, dt=float(c0['dt']), K=int(c0['K']), nb=int(c0['nb']), order=c0['order'],
-                   iso=bool(c0['iso']), basin=basin, north=north, tw=tw, so=so, ml=ml)
+                   iso=bool(c0['iso']), basin=basin, north=north, tw=tw, so=so, ml=ml, pac=pac,
+                   zoc_f=None if pac is None else stack(lambda c: c['zoc_f']),
+                   so_pac_L=None if pac is None else stack(lambda c: c['so_pac_L']))

@@ -18,7 +18,7 @@ def emu():
 
 
 @pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 720), ('twocol', 480), ('c3', 480), ('c4', 600), ('c4_literal', 120),
-                                       ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40)])
+                                       ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40), ('twobasin', 480)])
 def test_fused_kernel_vs_reference(emu, name, nmax):
   run_against_golden(emu, name, nmax)
 

@@ -17,7 +17,7 @@ from oracle import pymoc_oracle as O
 warnings.filterwarnings('ignore', category=RuntimeWarning)
 
 COUPLED = [('c1', 300), ('c2', 73), ('twocol', 25), ('c3', 25), ('c3_bvp', 25), ('c4', 13), ('c4_literal', 120),
-           ('c5', 25)]
+           ('c5', 25), ('twobasin', 25)]
 
 
 @pytest.mark.parametrize('name,nmax', COUPLED)
@@ -32,7 +32,8 @@ def test_coupled_loops_bit_exact(name, nmax):
         assert np.array_equal(got[key], val, equal_nan=True), (name, m, n, key)
 
 
-@pytest.mark.parametrize('name,n', [('c1', 300), ('c2', 720), ('twocol', 480), ('c3', 480), ('c4', 600), ('c5', 480)])
+@pytest.mark.parametrize('name,n', [('c1', 300), ('c2', 720), ('twocol', 480), ('c3', 480), ('c4', 600), ('c5', 480),
+                                    ('twobasin', 480)])
 def test_kernel_closed_forms_within_gate(name, n):
   """Exact quadrature / restated Brent / Thomas vs solve_bvp / brentq / inv: << 1e-10."""
   tree = golden(name)
