@@ -184,6 +184,9 @@ class PinnedHostBackend:
   def download(self, buf):
     return buf.numpy().copy()
 
+  def assign(self, buf, arr):
+    buf.numpy()[...] = arr
+
   def stream(self):
     return None
 

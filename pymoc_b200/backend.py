@@ -29,6 +29,9 @@ class CudaBackend:
   def download(self, buf):
     return buf.cpu().numpy()
 
+  def assign(self, buf, arr):
+    buf.copy_(self.torch.from_numpy(np.ascontiguousarray(arr)).view(buf.dtype).reshape(buf.shape))
+
   def stream(self):
     return self.torch.cuda.current_stream(self.device).cuda_stream
 

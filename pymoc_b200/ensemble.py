@@ -223,6 +223,19 @@ class Ensemble:
     keys = [k for k in ('b_basin', 'b_north', 'b_pac', 'bs_ml') if k in self._bufs]
     return {k: self.be.download(self._bufs[k]) for k in keys}
 
+  def set_state(self, **arrays):
+    """Overwrite prognostic arrays (``b_basin``, ``b_north``, ``b_pac``, ``bs_ml``; [M, n] each) in place
+    on the device -- the pickup path (examples/run_JansenNadeau_2018.py:135-138).  Cached
+    streamfunctions are discarded: the next run re-diagnoses them."""
+    for k, v in arrays.items():
+      if k not in ('b_basin', 'b_north', 'b_pac', 'bs_ml') or k not in self._bufs:
+        raise KeyError(k)
+      v = np.ascontiguousarray(v, dtype=np.float64)
+      if v.shape != tuple(self._bufs[k].shape):
+        raise ValueError('%s: shape %r, expected %r' % (k, v.shape, tuple(self._bufs[k].shape)))
+      self.be.assign(self._bufs[k], v)
+    self._diagnosed = False
+
   def diagnostics(self):
     self.be.sync()
     keys = [k for k in ('Psi_tw', 'Psi_iso_b', 'Psi_iso_n', 'psib', 'bgrid', 'Psi_so', 'Psi_Ek', 'Psi_GM', 'Psi_s',

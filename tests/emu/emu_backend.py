@@ -38,6 +38,9 @@ class EmuBackend:
   def download(self, buf):
     return buf.copy()
 
+  def assign(self, buf, arr):
+    buf[...] = arr
+
   def stream(self):
     return None
 

@@ -57,7 +57,7 @@ def _channel(z, so, b):
   return Psi_SO(z=z, y=so['y'], b=b, bs=so['bs'].copy(), tau=so['tau'], **kw)
 
 
-def run_reference(case, checkpoints):
+def run_reference(case, checkpoints, diag_iters=None):
   """Run the reference loop of ``case`` and snapshot the outputs after each N in
   ``checkpoints`` (ascending).  Statement order follows the cited scripts."""
   z, dt, K, nb = case['z'], case['dt'], case['K'], case['nb']
@@ -152,6 +152,7 @@ def run_reference(case, checkpoints):
     channel = SO_ML(y=m['y'], h=m['h'], L=m['L'], Ks=m['Ks'], surflux=m['surflux'].copy(),
                     rest_mask=m['rest_mask'].copy(), b_rest=m['b_rest'].copy(), v_pist=m['v_pist'],
                     bs=m['bs'].copy())
+    diag = {k: [] for k in ('AMOC', 'AMOC_b', 'b_basin', 'b_north', 'bs_SO', 'bgrid', 'Psi_SO')}
     for ii in range(max(checkpoints)):
       if ii % K == 0:
         AMOC.update(b1=basin.b, b2=north.b)
@@ -159,6 +160,14 @@ def run_reference(case, checkpoints):
         [Psi_res_b, Psi_res_n] = AMOC.Psibz(nb=nb)
         PsiSO.update(b=basin.b, bs=channel.bs)
         PsiSO.solve()
+        if diag_iters and ii % diag_iters == 0:  # run_JansenNadeau_2018.py:218-226
+          diag['AMOC'].append(AMOC.Psi.copy())
+          diag['AMOC_b'].append(AMOC.Psib(nb=nb).copy())
+          diag['bgrid'].append(AMOC.bgrid.copy())
+          diag['b_basin'].append(basin.b.copy())
+          diag['b_north'].append(north.b.copy())
+          diag['bs_SO'].append(channel.bs.copy())
+          diag['Psi_SO'].append(PsiSO.Psi.copy())
       wAb = (Psi_res_b - PsiSO.Psi) * 1e6
       wAN = -Psi_res_n * 1e6
       if PsiSO.Psi[1] < 0:
@@ -181,6 +190,13 @@ def run_reference(case, checkpoints):
       channel.timestep(b_basin=basin.b, Psi_b=PsiSO.Psi, dt=dt)
       if ii + 1 in checkpoints:
         snapshot(ii + 1, AMOC, PsiSO, [Psi_res_b, Psi_res_n], channel)
+    if diag_iters:
+      col = lambda k: np.stack(diag[k], axis=-1)
+      # positional layout of np.savez(diagfile, ...) at :268-272 and of the pickup at :266-267
+      snaps['diagfile'] = {'arr_%d' % i: a for i, a in enumerate(
+          [col('AMOC'), col('AMOC_b'), col('b_basin'), col('b_north'), col('bs_SO'), z, col('bgrid'), so['y'],
+           col('Psi_SO'), np.float64(so['tau']), np.float64(so['KGM'])])}
+      snaps['pickup'] = {'arr_0': basin.b.copy(), 'arr_1': north.b.copy(), 'arr_2': channel.bs.copy()}
   return snaps
 
 
@@ -390,6 +406,12 @@ if __name__ == '__main__':
     coupled_fixture('c4.npz', configs.c4_jansen_nadeau(32, axes=(2, 2, 2, 2, 2)), [0, 13, 22, 31], [1, 12, 13, 600, 2400])
   if want('c4_literal'):
     coupled_fixture('c4_literal.npz', configs.c4_jansen_nadeau(1), [0], [1, 120, 1200])
+  if want('c4_diags'):  # the diagnostics / pickup files of the literal script, 360 iterations, Diag_iters = 120
+    spec = configs.c4_jansen_nadeau(1)
+    case = spec.member_case(0)
+    tree = dict(versions=VERSIONS, name=spec.name, case=case, diag_iters=120, total_iters=360,
+                files=run_reference(case, [360], diag_iters=120))
+    save_tree(os.path.join(HERE, 'c4_diags.npz'), tree)
   if want('twobasin'):
     coupled_fixture('twobasin.npz', configs.twobasin(8, axes=(2, 2, 2)), [0, 5, 7], [1, 25, 480, 1200])
   if want('c5'):

@@ -39,3 +39,35 @@ def run_against_golden(backend, name, nmax, tol=TOL, chunked=False):
 
 def unit_column(backend, lib_call):
   pass
+
+
+def diag_and_pickup_files(backend, tmpdir):
+  """The --diagfile / --pickup_save_file archives of examples/run_JansenNadeau_2018.py:266-272 for
+  the literal script configuration, 360 iterations with Diag_iters = 120, against the files the
+  reference writes (golden c4_diags.npz); then a restart from the pickup."""
+  import os
+
+  from pymoc_b200 import pickup
+  tree = golden('c4_diags')
+  ens = Ensemble(spec_from_cases([tree['case']]), backend=backend)
+  rec = pickup.DiagRecorder(ens, int(tree['diag_iters'])).run(int(tree['total_iters']))
+  dpath, ppath = os.path.join(tmpdir, 'diags.npz'), os.path.join(tmpdir, 'pickup.npz')
+  rec.save(dpath, member=0)
+  pickup.save_pickup(ens, ppath, member=0)
+  got, want = np.load(dpath), tree['files']['diagfile']
+  assert sorted(got.files) == sorted(want), (got.files, sorted(want))
+  for k in want:
+    assert np.shape(got[k]) == np.shape(want[k]), (k, np.shape(got[k]), np.shape(want[k]))
+    assert relmax(got[k], want[k]) < TOL, (k, relmax(got[k], want[k]))
+  gotp = np.load(ppath)
+  for k, v in tree['files']['pickup'].items():
+    assert relmax(gotp[k], v) < TOL, k
+  # restart: a fresh ensemble picked up from the file continues like the one that wrote it
+  # (the scripts restart their iteration counter, so 360 must be -- and is -- a multiple of K)
+  again = Ensemble(spec_from_cases([tree['case']]), backend=backend)
+  pickup.load_pickup(again, ppath)
+  assert again.it == 0
+  again.run(24)
+  ens.run(24)
+  for k, v in ens.state().items():
+    assert np.array_equal(v, again.state()[k]), k

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from emu.emu_backend import EmuBackend
-from parity_common import run_against_golden
+from parity_common import diag_and_pickup_files, run_against_golden
 
 
 @pytest.fixture(scope='module')
@@ -33,3 +33,7 @@ def test_f2010_smoother_literal_c3(emu):
   solve_bvp (tol=1e-3) against the converged solution of the same ODE; stated tolerance 1e-5."""
   worst = run_against_golden(emu, 'c3_bvp', 240, tol=1e-5)
   assert worst > 1e-12  # the two are different discretisations; a tiny number would mean the test is vacuous
+
+
+def test_diagnostics_and_pickup_wire_format(emu, tmp_path):
+  diag_and_pickup_files(emu, str(tmp_path))

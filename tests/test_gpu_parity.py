@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from helpers import relmax
-from parity_common import TOL, run_against_golden
+from parity_common import TOL, diag_and_pickup_files, run_against_golden
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings('ignore', category=RuntimeWarning)
@@ -103,3 +103,7 @@ def test_host_buffer_entry_point(cuda):
     assert np.array_equal(val, host.state()[key]), key
   for key in ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib'):
     assert np.array_equal(dev.diagnostics()[key], host.diagnostics()[key]), key
+
+
+def test_diagnostics_and_pickup_wire_format(cuda, tmp_path):
+  diag_and_pickup_files(cuda, str(tmp_path))
