@@ -418,6 +418,13 @@ PM_DEV int bgrid_count_le(const BGrid& G, double v) {
 // every cell exceptional.
 // Scratch: rs = 6*nzp doubles, psib_s = nb doubles, cnt_s = nb+1 ints, all owned by this warp.
 
+// flat cells sitting exactly on a class value: 0/0 = NaN in the reference (psi_thermwind.py:183)
+PM_COLD double remap_flat_fix(double c, double x, int k, int nz, const double* b_s, const double* w_s) {
+  for (int cc = k; cc + 1 < nz && b_s[cc + 1] == x; ++cc)
+    if (w_s[cc] != 0.0) c = NAN;
+  return c;
+}
+
 template <int LPL>
 PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const double (&b2)[LPL], int nz, int nb,
                      double* rs, double* psib_s, int* cnt_s) {
@@ -620,17 +627,13 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
         const double bk = b1_s[k1];
         c1 = S1_s[k1];
         if (k1 > 0 && bk != x) c1 = c1 + (bk - x) * w1_s[k1 - 1];
-        if (bk == x)  // flat cells sitting exactly on the class: 0/0 in the reference
-          for (int c = k1; c + 1 < nz && b1_s[c + 1] == x; ++c)
-            if (w1_s[c] != 0.0) c1 = NAN;
+        if (bk == x) c1 = remap_flat_fix(c1, x, k1, nz, b1_s, w1_s);
       }
       if (k2 < nz) {
         const double bk = b2_s[k2];
         c2 = S2_s[k2];
         if (k2 > 0 && bk != x) c2 = c2 + (bk - x) * w2_s[k2 - 1];
-        if (bk == x)
-          for (int c = k2; c + 1 < nz && b2_s[c + 1] == x; ++c)
-            if (w2_s[c] != 0.0) c2 = NAN;
+        if (bk == x) c2 = remap_flat_fix(c2, x, k2, nz, b2_s, w2_s);
       }
       psib_s[i] = E > 0 ? psib_s[i] + (c1 + c2) : c1 + c2;
     }
@@ -1069,14 +1072,20 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
       ysv[j] = yo;
     }
   }
-  double dyv[LPL];
+  double dyv[LPL], prev[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) prev[j] = pre0;
+  if (P.tau_y != nullptr) {  // tau on the y grid: a 100-point mean and two divides per level (kept out of the float-tau path)
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j)
+      if (lev<LPL>(j) < nz) prev[j] = tau_mean100(ysv[j], S.yN, ygrid, P.tau_y, ny) / P.f / P.rho * P.L;
+  }
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j), s = lm(j);
     const bool in = i < nz;
     const double yo = in ? ysv[j] : 0.0;
-    double pre = pre0;
-    if (P.tau_y != nullptr && in) pre = tau_mean100(yo, S.yN, ygrid, P.tau_y, ny) / P.f / P.rho * P.L;
+    const double pre = prev[j];
     const double e = div_const(pre * P.sill[s] * P.ektap[s], c6, r6);
     double dy = S.yN - yo;
     dy = 0.1 > dy ? 0.1 : dy;

@@ -5,10 +5,18 @@
 #ifndef PM_LPL
 #error "compile with -DPM_LPL=<levels per lane>"
 #endif
+#ifndef PM_MINB_SMALL
+#define PM_MINB_SMALL 4
+#endif
 
 namespace pmk {
+// resident CTAs per SM the register allocation aims at.  Five (96 registers, 20 warps/SM) fit the
+// single-column topologies' shared memory, but measured slower on C2 (0.72 vs 0.76 of the roofline):
+// the spills of the tighter budget cost more than the extra warps hide.  -DPM_MINB_SMALL=5 to retry.
+constexpr int min_ctas(unsigned topo) { return (topo & (PMOC_HAS_NORTH | PMOC_HAS_ML | PMOC_SO_BVP)) ? 4 : PM_MINB_SMALL; }
+
 template <int LPL, unsigned TOPO>
-PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, 4) k_model(RunArgs a) {
+PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, min_ctas(TOPO)) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
