@@ -37,3 +37,20 @@ def test_f2010_smoother_literal_c3(emu):
 
 def test_diagnostics_and_pickup_wire_format(emu, tmp_path):
   diag_and_pickup_files(emu, str(tmp_path))
+
+
+def test_jn_split_launches_bitwise(emu):
+  """'jn' order: a run split into launches at and between diagnosis iterations equals the single launch."""
+  import numpy as np
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  spec = configs.c4_jansen_nadeau(4, axes=(2, 2, 1, 1, 1))
+  a = Ensemble(spec, backend=emu)
+  a.run(37)
+  b = Ensemble(spec, backend=emu)
+  for c in (12, 7, 18):
+    b.run(c)
+  for k, v in a.state().items():
+    assert np.array_equal(v, b.state()[k], equal_nan=True), k
+  for k in ('Psi_iso_b', 'Psi_so', 'bbot_basin', 'bbot_north'):
+    assert np.array_equal(a.diagnostics()[k], b.diagnostics()[k], equal_nan=True), k

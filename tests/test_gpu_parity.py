@@ -107,3 +107,57 @@ def test_host_buffer_entry_point(cuda):
 
 def test_diagnostics_and_pickup_wire_format(cuda, tmp_path):
   diag_and_pickup_files(cuda, str(tmp_path))
+
+
+def test_full_size_c3_properties(cuda):
+  """BASELINE configs[2] size (262,144 members of the two-column + Psi_SO model): (1) splitting a run into
+  launches changes nothing bit-wise (the carried streamfunctions are exact copies); (2) members that differ
+  only in a parameter the northern column does not see ... all members distinct, all finite; (3) boundary
+  values are the exact copies the reference makes; (4) every sampled member matches the live oracle."""
+  from oracle import pymoc_oracle as O
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  M = 262144
+  spec = configs.c3_twocol_so(M)
+  a = Ensemble(spec, backend=cuda)
+  a.run(49)
+  b = Ensemble(spec, backend=cuda)
+  for n in (24, 1, 24):
+    b.run(n)
+  sa, sb = a.state(), b.state()
+  for k in sa:
+    assert np.array_equal(sa[k], sb[k]), k
+  da, db = a.diagnostics(), b.diagnostics()
+  for k in ('Psi_tw', 'Psi_iso_b', 'Psi_iso_n', 'Psi_so', 'psib'):
+    assert np.array_equal(da[k], db[k]), k
+  assert not (da['status'] & 1).any()
+  assert np.isfinite(sa['b_basin']).all() and np.isfinite(sa['b_north']).all()
+  assert np.all(sa['b_basin'][:, -1] == 0.03) and np.all(sa['b_basin'][:, 0] == 0.0)
+  assert np.all(da['Psi_so'][:, 0] == 0.0) and np.all(da['Psi_tw'][:, 0] == 0.0)
+  for m in (0, 12345, 99999, M - 1):
+    want = O.run_coupled(spec.member_case(m), 49, O.REFERENCE)
+    for key in ('b_basin', 'b_north', 'Psi_iso_b', 'Psi_so'):
+      got = sa[key][m] if key in sa else da[key][m]
+      assert relmax(got, want[key]) < TOL, (m, key, relmax(got, want[key]))
+
+
+def test_jn_and_wide_split_launches_bitwise(cuda):
+  """'jn' order (C4, 65,536 members) and the block-per-member kernels (nz = 320): a run split into
+  launches at and between diagnosis iterations equals the single launch bit for bit, including the
+  carried bottom-boundary switches (bbot, kappa variant) and the mixed layer."""
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  for spec, n, cuts in ((configs.c4_jansen_nadeau(65536), 61, (12, 7, 30, 12)),
+                        (configs.c5_single_global_basin(128, nz=320, dt_days=1., kapfac_max=1.), 1450, (720, 5, 725))):
+    a = Ensemble(spec, backend=cuda)
+    a.run(n)
+    b = Ensemble(spec, backend=cuda)
+    assert sum(cuts) == n
+    for c in cuts:
+      b.run(c)
+    sa, sb = a.state(), b.state()
+    for k in sa:
+      assert np.array_equal(sa[k], sb[k], equal_nan=True), (spec.name, k)
+    da, db = a.diagnostics(), b.diagnostics()
+    for k in ('Psi_iso_b', 'Psi_iso_n', 'Psi_so', 'bbot_basin', 'bbot_north'):
+      assert np.array_equal(da[k], db[k], equal_nan=True), (spec.name, k)
