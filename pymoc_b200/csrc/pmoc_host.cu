@@ -6,68 +6,102 @@
 #ifndef PMOC_EMU
 namespace {
 
-// Mirrors host arrays of a pmoc_model on the device for the duration of one call.
+// Mirrors the host arrays of a pmoc_model on the device for the duration of one call, and pipelines the
+// call over blocks of members: block c's host->device copies, kernel and device->host copies are queued on
+// stream c % kStreams, so the copies of one block overlap the kernel of another (members are independent).
+constexpr int kStreams = 3;
+
 struct Mirror {
-  cudaStream_t s = nullptr;
-  struct Back { void* host; void* dev; size_t bytes; };
+  struct Field {
+    char* host;        // host base
+    char* dev;         // device base
+    size_t slot;       // byte offset of the pointer inside pmoc_model
+    size_t per_member; // bytes per member; 0 = shared by all members
+    size_t bytes;      // total bytes
+    bool in, out;      // copied in / copied back
+  };
+  cudaStream_t s[kStreams] = {};
+  cudaEvent_t shared_ready = nullptr;
+  std::vector<Field> fields;
   std::vector<void*> allocs;
-  std::vector<Back> backs;
   cudaError_t err = cudaSuccess;
+  const pmoc_model* h;
+  pmoc_model d;
 
   void* alloc(size_t bytes) {
-    void* d = nullptr;
-    if (err == cudaSuccess) err = cudaMallocAsync(&d, bytes ? bytes : 8, s);
-    if (d) allocs.push_back(d);
-    return d;
+    void* p = nullptr;
+    if (err == cudaSuccess) err = cudaMallocAsync(&p, bytes ? bytes : 8, s[0]);
+    if (p) allocs.push_back(p);
+    return p;
   }
-  // input: upload
+  // register the pointer stored at `slot` of the model (hp: its host value)
+  template <class P>
+  void add(P* slot, const void* hp, size_t per_member, size_t bytes, bool in, bool out) {
+    if (!hp) return;
+    char* dp = static_cast<char*>(alloc(bytes));
+    fields.push_back({(char*)hp, dp, (size_t)((char*)slot - (char*)&d), per_member, bytes, in, out});
+    *slot = reinterpret_cast<P>(dp);
+  }
+  void vec(pmoc_vec* dv, long long M, size_t len) {  // input vector: per member when mstride != 0
+    if (!dv->ptr) return;
+    const size_t stride = (size_t)dv->mstride * sizeof(double);
+    const size_t bytes = stride ? (size_t)(M - 1) * stride + len * sizeof(double) : len * sizeof(double);
+    add(&dv->ptr, dv->ptr, stride, bytes, true, false);
+  }
   template <class T>
-  const T* in(const T* h, size_t n) {
-    if (!h) return nullptr;
-    void* d = alloc(n * sizeof(T));
-    if (d && err == cudaSuccess) err = cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
-    return static_cast<const T*>(d);
-  }
-  pmoc_vec in(pmoc_vec v, long long M, size_t len) {
-    if (!v.ptr) return v;
-    const size_t n = v.mstride ? (size_t)(M - 1) * (size_t)v.mstride + len : len;
-    return pmoc_vec{in(v.ptr, n), v.mstride};
-  }
-  // output (optionally also an input): copied back at the end
+  void shared(const T** dp, size_t n) { add(dp, *dp, 0, n * sizeof(T), true, false); }
   template <class T>
-  T* out(T* h, size_t n, bool upload) {
-    if (!h) return nullptr;
-    void* d = alloc(n * sizeof(T));
-    if (d && err == cudaSuccess) {
-      err = upload ? cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, s)
-                   : cudaMemsetAsync(d, 0, n * sizeof(T), s);
-      backs.push_back({h, d, n * sizeof(T)});
+  void state(T** dp, long long M, size_t len, bool upload) {  // per-member output, optionally also input
+    add(dp, *dp, len * sizeof(T), (size_t)M * len * sizeof(T), upload, true);
+  }
+  void column(pmoc_column* c, long long M, int nz) {
+    state(&c->b, M, nz, true);
+    vec(&c->kappa, M, (size_t)c->nvar * nz);
+    vec(&c->dAk, M, (size_t)c->nvar * nz);
+    vec(&c->Area, M, nz);
+    vec(&c->bs, M, 1);
+    vec(&c->N2min, M, 1);
+    vec(&c->bzbot, M, 1);
+    state(&c->bbot, M, 1, true);
+    state(&c->var, M, 1, true);
+  }
+  void upload_shared() {
+    for (auto& f : fields)
+      if (!f.per_member && f.in && err == cudaSuccess)
+        err = cudaMemcpyAsync(f.dev, f.host, f.bytes, cudaMemcpyHostToDevice, s[0]);
+    if (err == cudaSuccess) err = cudaEventRecord(shared_ready, s[0]);
+  }
+  // members [m0, m0+n) in, on stream st; the last member of an input vector may be shorter than its stride
+  void upload_block(long long m0, long long n, long long M, cudaStream_t st) {
+    for (auto& f : fields) {
+      if (!f.per_member || err != cudaSuccess) continue;
+      const size_t off = (size_t)m0 * f.per_member;
+      size_t len = (size_t)n * f.per_member;
+      if (off + len > f.bytes) len = f.bytes - off;
+      err = f.in ? cudaMemcpyAsync(f.dev + off, f.host + off, len, cudaMemcpyHostToDevice, st)
+                 : cudaMemsetAsync(f.dev + off, 0, len, st);
     }
-    return static_cast<T*>(d);
   }
-  void copy_back() {
-    for (auto& b : backs)
-      if (err == cudaSuccess) err = cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, s);
+  void download_block(long long m0, long long n, cudaStream_t st) {
+    for (auto& f : fields) {
+      if (!f.per_member || !f.out || err != cudaSuccess) continue;
+      const size_t off = (size_t)m0 * f.per_member;
+      err = cudaMemcpyAsync(f.host + off, f.dev + off, (size_t)n * f.per_member, cudaMemcpyDeviceToHost, st);
+    }
+  }
+  // the device model restricted to members [m0, m0+n)
+  pmoc_model block_model(long long m0, long long n) const {
+    pmoc_model b = d;
+    b.M = n;
+    for (auto& f : fields)
+      if (f.per_member) *reinterpret_cast<char**>((char*)&b + f.slot) = f.dev + (size_t)m0 * f.per_member;
+    return b;
   }
   void release() {
-    for (void* d : allocs) cudaFreeAsync(d, s);
+    for (void* p : allocs) cudaFreeAsync(p, s[0]);
     allocs.clear();
   }
 };
-
-pmoc_column mirror_column(Mirror& mr, const pmoc_column& c, long long M, int nz) {
-  pmoc_column d = c;
-  d.b = mr.out(c.b, (size_t)M * nz, true);
-  d.kappa = mr.in(c.kappa, M, (size_t)c.nvar * nz);
-  d.dAk = mr.in(c.dAk, M, (size_t)c.nvar * nz);
-  d.Area = mr.in(c.Area, M, nz);
-  d.bs = mr.in(c.bs, M, 1);
-  d.N2min = mr.in(c.N2min, M, 1);
-  d.bzbot = mr.in(c.bzbot, M, 1);
-  d.bbot = mr.out(c.bbot, (size_t)M, true);
-  d.var = mr.out(c.var, (size_t)M, true);
-  return d;
-}
 
 }  // namespace
 #endif
@@ -92,70 +126,102 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
     PM_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
     PM_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
-  PM_CUDA_OK(cudaStreamCreateWithFlags(&mr.s, cudaStreamNonBlocking));
-  pmoc_model d = *m;
+  for (int i = 0; i < kStreams; ++i) PM_CUDA_OK(cudaStreamCreateWithFlags(&mr.s[i], cudaStreamNonBlocking));
+  PM_CUDA_OK(cudaEventCreateWithFlags(&mr.shared_ready, cudaEventDisableTiming));
+  mr.h = m;
+  mr.d = *m;
+  pmoc_model& d = mr.d;
   const bool carry = it0 > 0;  // streamfunctions diagnosed by an earlier call are inputs
-  d.z = mr.in(m->z, nz);
-  d.y = mr.in(m->y, ny);
-  d.basin = mirror_column(mr, m->basin, M, nz);
-  if (f & PMOC_HAS_NORTH) d.north = mirror_column(mr, m->north, M, nz);
+  mr.shared(&d.z, nz);
+  mr.shared(&d.y, ny);
+  mr.column(&d.basin, M, nz);
+  if (f & PMOC_HAS_NORTH) mr.column(&d.north, M, nz);
   if (f & PMOC_HAS_PAC) {
-    d.pac = mirror_column(mr, m->pac, M, nz);
-    d.zoc_f = mr.in(m->zoc_f, M, 1);
-    d.so2_L = mr.in(m->so2_L, M, 1);
-    d.Psi_zoc = mr.out(m->Psi_zoc, (size_t)M * nz, carry);
-    d.Psi_zon_a = mr.out(m->Psi_zon_a, (size_t)M * nz, carry);
-    d.Psi_zon_p = mr.out(m->Psi_zon_p, (size_t)M * nz, carry);
-    d.psib2 = mr.out(m->psib2, (size_t)M * nb, carry);
-    d.bgrid2 = mr.out(m->bgrid2, (size_t)M * nb, carry);
-    d.Psi_so2 = mr.out(m->Psi_so2, (size_t)M * nz, carry);
-    d.Psi_Ek2 = mr.out(m->Psi_Ek2, (size_t)M * nz, carry);
-    d.Psi_GM2 = mr.out(m->Psi_GM2, (size_t)M * nz, carry);
+    mr.column(&d.pac, M, nz);
+    mr.vec(&d.zoc_f, M, 1);
+    mr.vec(&d.so2_L, M, 1);
+    mr.state(&d.Psi_zoc, M, nz, carry);
+    mr.state(&d.Psi_zon_a, M, nz, carry);
+    mr.state(&d.Psi_zon_p, M, nz, carry);
+    mr.state(&d.psib2, M, nb, carry);
+    mr.state(&d.bgrid2, M, nb, carry);
+    mr.state(&d.Psi_so2, M, nz, carry);
+    mr.state(&d.Psi_Ek2, M, nz, carry);
+    mr.state(&d.Psi_GM2, M, nz, carry);
   }
-  d.tw_f = mr.in(m->tw_f, M, 1);
-  d.tw_b2 = mr.in(m->tw_b2, M, nz);
-  d.so_bs = mr.in(m->so_bs, M, ny);
-  d.so_tau = mr.in(m->so_tau, M, m->so_tau_on_y ? ny : 1);
-  d.so_f = mr.in(m->so_f, M, 1);
-  d.so_rho = mr.in(m->so_rho, M, 1);
-  d.so_L = mr.in(m->so_L, M, 1);
-  d.so_KGM = mr.in(m->so_KGM, M, 1);
-  d.so_smax = mr.in(m->so_smax, M, 1);
-  d.so_c = mr.in(m->so_c, M, 1);
-  d.so_sill_taper = mr.in(m->so_sill_taper, nz);
-  d.so_ek_taper = mr.in(m->so_ek_taper, nz);
-  d.so_top_taper = mr.in(m->so_top_taper, nz);
-  d.so_bot_taper = mr.in(m->so_bot_taper, nz);
-  d.ml_bs = mr.out(m->ml_bs, (size_t)M * ny, true);
-  d.ml_Ks = mr.in(m->ml_Ks, M, 1);
-  d.ml_h = mr.in(m->ml_h, M, 1);
-  d.ml_L = mr.in(m->ml_L, M, 1);
-  d.ml_vpist = mr.in(m->ml_vpist, M, 1);
-  d.ml_surflux = mr.in(m->ml_surflux, M, ny);
-  d.ml_rest_mask = mr.in(m->ml_rest_mask, M, ny);
-  d.ml_b_rest = mr.in(m->ml_b_rest, M, ny);
-  d.Psi_tw = mr.out(m->Psi_tw, (size_t)M * nz, carry);
-  d.Psi_iso_b = mr.out(m->Psi_iso_b, (size_t)M * nz, carry);
-  d.Psi_iso_n = mr.out(m->Psi_iso_n, (size_t)M * nz, carry);
-  d.psib = mr.out(m->psib, (size_t)M * nb, carry);
-  d.bgrid = mr.out(m->bgrid, (size_t)M * nb, carry);
-  d.Psi_so = mr.out(m->Psi_so, (size_t)M * nz, carry);
-  d.Psi_Ek = mr.out(m->Psi_Ek, (size_t)M * nz, carry);
-  d.Psi_GM = mr.out(m->Psi_GM, (size_t)M * nz, carry);
-  d.ml_Psi_s = mr.out(m->ml_Psi_s, (size_t)M * ny, carry);
-  d.status = mr.out(m->status, (size_t)M, true);
+  mr.vec(&d.tw_f, M, 1);
+  mr.vec(&d.tw_b2, M, nz);
+  mr.vec(&d.so_bs, M, ny);
+  mr.vec(&d.so_tau, M, m->so_tau_on_y ? ny : 1);
+  mr.vec(&d.so_f, M, 1);
+  mr.vec(&d.so_rho, M, 1);
+  mr.vec(&d.so_L, M, 1);
+  mr.vec(&d.so_KGM, M, 1);
+  mr.vec(&d.so_smax, M, 1);
+  mr.vec(&d.so_c, M, 1);
+  mr.shared(&d.so_sill_taper, nz);
+  mr.shared(&d.so_ek_taper, nz);
+  mr.shared(&d.so_top_taper, nz);
+  mr.shared(&d.so_bot_taper, nz);
+  mr.state(&d.ml_bs, M, ny, true);
+  mr.vec(&d.ml_Ks, M, 1);
+  mr.vec(&d.ml_h, M, 1);
+  mr.vec(&d.ml_L, M, 1);
+  mr.vec(&d.ml_vpist, M, 1);
+  mr.vec(&d.ml_surflux, M, ny);
+  mr.vec(&d.ml_rest_mask, M, ny);
+  mr.vec(&d.ml_b_rest, M, ny);
+  mr.state(&d.Psi_tw, M, nz, carry);
+  mr.state(&d.Psi_iso_b, M, nz, carry);
+  mr.state(&d.Psi_iso_n, M, nz, carry);
+  mr.state(&d.psib, M, nb, carry);
+  mr.state(&d.bgrid, M, nb, carry);
+  mr.state(&d.Psi_so, M, nz, carry);
+  mr.state(&d.Psi_Ek, M, nz, carry);
+  mr.state(&d.Psi_GM, M, nz, carry);
+  mr.state(&d.ml_Psi_s, M, ny, carry);
+  mr.state(&d.status, M, 1, true);
+  // blocks of members: enough of them to overlap copies with kernels, each large enough to fill the GPU
+  long long nblk = M / 8192;
+  if (nblk < 1) nblk = 1;
+  if (nblk > 16) nblk = 16;
+  const long long per = (M + nblk - 1) / nblk;
+  void* scratch[kStreams] = {};
   d.scratch = nullptr;
-  d.scratch_bytes = pmoc_model_scratch_bytes(m);
-  if (d.scratch_bytes) d.scratch = mr.alloc((size_t)d.scratch_bytes);
+  d.scratch_bytes = 0;
+  {  // block-per-member kernels (nz > 256): one scratch buffer per stream, sized for a block
+    pmoc_model one = *m;
+    one.M = per;
+    const uint64_t need = pmoc_model_scratch_bytes(&one);
+    if (need) {
+      for (int i = 0; i < kStreams && i < nblk; ++i) scratch[i] = mr.alloc((size_t)need);
+      d.scratch_bytes = need;
+    }
+  }
   int rc = PMOC_OK;
   if (mr.err == cudaSuccess) {
-    if (it0 == 0 && !(f & PMOC_ORDER_JN)) rc = pmoc_model_diagnose(&d, mr.s);
-    if (rc == PMOC_OK) rc = pmoc_model_run(&d, it0, nsteps, mr.s);
-    if (rc == PMOC_OK) mr.copy_back();
+    mr.upload_shared();
+    for (int i = 1; i < kStreams && mr.err == cudaSuccess; ++i) mr.err = cudaStreamWaitEvent(mr.s[i], mr.shared_ready, 0);
+    for (long long c = 0; c < nblk && rc == PMOC_OK && mr.err == cudaSuccess; ++c) {
+      const long long m0 = c * per, n = (m0 + per <= M ? per : M - m0);
+      if (n <= 0) break;
+      cudaStream_t st = mr.s[c % kStreams];
+      mr.upload_block(m0, n, M, st);
+      pmoc_model blk = mr.block_model(m0, n);
+      blk.scratch = scratch[c % kStreams];
+      if (it0 == 0 && !(f & PMOC_ORDER_JN)) rc = pmoc_model_diagnose(&blk, st);
+      if (rc == PMOC_OK) rc = pmoc_model_run(&blk, it0, nsteps, st);
+      if (rc == PMOC_OK) mr.download_block(m0, n, st);
+    }
   }
-  mr.release();
-  cudaError_t e = cudaStreamSynchronize(mr.s);
-  cudaStreamDestroy(mr.s);
+  cudaError_t e = cudaSuccess;
+  for (int i = kStreams - 1; i >= 0; --i) {  // stream 0 last: it owns the allocations
+    if (i == 0) mr.release();
+    const cudaError_t ei = cudaStreamSynchronize(mr.s[i]);
+    if (e == cudaSuccess) e = ei;
+  }
+  for (int i = 0; i < kStreams; ++i) cudaStreamDestroy(mr.s[i]);
+  cudaEventDestroy(mr.shared_ready);
   if (rc != PMOC_OK) return rc;
   PM_CUDA_OK(mr.err);
   PM_CUDA_OK(e);

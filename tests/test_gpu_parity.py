@@ -93,16 +93,19 @@ def test_host_buffer_entry_point(cuda):
     def __init__(self, lib):
       self.lib = lib
 
-  spec = configs.c3_twocol_so(16, axes=(2, 2, 2, 2))
-  dev = Ensemble(spec, backend=cuda)
-  dev.run(30)
-  host = Ensemble(spec, backend=HostBuffers(cuda.lib))
-  _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 0, 13))
-  _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 13, 17))
-  for key, val in dev.state().items():
-    assert np.array_equal(val, host.state()[key]), key
-  for key in ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib'):
-    assert np.array_equal(dev.diagnostics()[key], host.diagnostics()[key]), key
+  # 16 members: one block; 32,768 members: four blocks pipelined over three streams
+  for spec, keys in ((configs.c3_twocol_so(16, axes=(2, 2, 2, 2)), ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib')),
+                     (configs.c2_column_so(32768), ('Psi_so', 'Psi_Ek', 'Psi_GM')),
+                     (configs.c4_jansen_nadeau(16384), ('Psi_iso_b', 'Psi_so', 'Psi_s', 'bbot_basin'))):
+    dev = Ensemble(spec, backend=cuda)
+    dev.run(30)
+    host = Ensemble(spec, backend=HostBuffers(cuda.lib))
+    _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 0, 13))
+    _lib.check(cuda.lib.pmoc_model_run_host(ctypes.byref(host.model), 13, 17))
+    for key, val in dev.state().items():
+      assert np.array_equal(val, host.state()[key], equal_nan=True), key
+    for key in keys:
+      assert np.array_equal(dev.diagnostics()[key], host.diagnostics()[key], equal_nan=True), key
 
 
 def test_diagnostics_and_pickup_wire_format(cuda, tmp_path):
