@@ -205,6 +205,8 @@ def gpu_arm(args):
   world = int(os.environ.get('WORLD_SIZE', 1))
   local = int(os.environ.get('LOCAL_RANK', 0))
   torch.cuda.set_device(local)
+  if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
   if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
   lib = _lib.lib()
@@ -213,9 +215,10 @@ def gpu_arm(args):
   m_local = args.members or m_default
   nt = args.nt or nt_default
   M = m_local * world
-  spec = build(M)
   lo, hi = shard_range(M, rank, world)
-  ens = Ensemble(spec, members=(lo, hi))
+  with configs.members(lo, hi):  # only this rank's block of the M-member lattice is ever built
+    spec = build(M)
+  ens = Ensemble(spec)
 
   peak = ctypes.c_double()
   mhz = ctypes.c_double()
@@ -262,7 +265,7 @@ def gpu_arm(args):
   e2e = None
   if args.e2e_steps > 0:
     hb = PinnedHostBackend(lib)
-    hens = Ensemble(spec, backend=hb, members=(lo, hi))
+    hens = Ensemble(spec, backend=hb)
     _lib.check(lib.pmoc_model_run_host(ctypes.byref(hens.model), 0, nt))  # warm-up (allocator pools)
     barrier()
     t0 = time.perf_counter()
@@ -298,7 +301,7 @@ def gpu_arm(args):
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': '%s: %s' % (args.workload, spec.name), 'members_per_gpu': m_local, 'members': M,
                    'nz': spec.nz, 'ny': spec.ny, 'K': spec.K, 'dt_days': spec.dt / 86400.,
-                   'model_steps_per_bench_step': nt, 'nan_members_rank0': nan_members, 'sweep': {k: [float(v.min()), float(v.max())] for k, v in spec.sweep.items()},
+                   'model_steps_per_bench_step': nt, 'nan_members_rank0': nan_members, 'sweep_rank0': {k: [float(v.min()), float(v.max())] for k, v in spec.sweep.items()},
                    'l2': 'inputs (state + per-member parameters, %.0f MB per GPU) larger than the 126 MB L2'
                          % (ens.M * spec.nz * 8 * 3 / 1e6),
                    'parallelism': 'ensemble members sharded over %d GPU(s), no collective in the loop' % world},
@@ -307,6 +310,10 @@ def gpu_arm(args):
                      'traffic': (NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
                                  if args.workload in NCU_TRAFFIC else None),
                      'traffic_source': 'bytes per launch (dram read + write), profiles/r1m_full_summary.txt',
+                     'hbm_check': (None if args.workload not in NCU_TRAFFIC else {
+                         'achieved_GBs': NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
+                                         / (ms_per_step * 1e-3) / 1e9,
+                         'peak_GBs': 6540.5, 'note': 'MEASURED_PEAKS.json hbm_gbs; state stays on chip, HBM is idle'}),
                      'flops_per_member_step': flops, 'peak_source': 'pmoc_fp64_peak measured live (DFMA stream)',
                      'kernel_ms': ms_per_step},
         'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': args.steps, 'clocks': clocks,

@@ -22,6 +22,39 @@ def lattice(**axes):
   return {n: np.ascontiguousarray(g.ravel()) for n, g in zip(names, grids)}
 
 
+_SHARD = None
+
+
+class members:
+  """``with configs.members(lo, hi): spec = configs.c2_column_so(M)`` builds only members [lo, hi) of the
+  M-member lattice (``spec.M == hi - lo``): what one rank of a sharded run needs, without ever materialising
+  the [M, nz] parameter arrays of the other ranks."""
+
+  def __init__(self, lo, hi):
+    self.block = (int(lo), int(hi))
+
+  def __enter__(self):
+    global _SHARD
+    self.prev, _SHARD = _SHARD, self.block
+    return self
+
+  def __exit__(self, *exc):
+    global _SHARD
+    _SHARD = self.prev
+
+
+def _shard(sweep, M):
+  """Check the lattice size and restrict it to the block selected by :class:`members`."""
+  n = next(iter(sweep.values())).size if sweep else M
+  assert n == M, (n, M)
+  if _SHARD is None or not sweep:
+    return sweep, M
+  lo, hi = _SHARD
+  if not (0 <= lo < hi <= M):
+    raise ValueError('member block %r outside the %d-member lattice' % (_SHARD, M))
+  return {k: np.ascontiguousarray(v[lo:hi]) for k, v in sweep.items()}, hi - lo
+
+
 def _sizes(M, naxes):
   """Split M (a power of two) into ``naxes`` near-equal power-of-two factors."""
   e = int(round(np.log2(M)))
@@ -65,6 +98,7 @@ def c2_column_so(M=65536, nz=200, ny=40, dt_days=10., ntau=None):
   nkap = M // ntau
   sweep = lattice(tau=np.linspace(0.05, 0.25, ntau) if ntau > 1 else [0.13],
                   kappa=np.geomspace(1e-5, 1e-4, nkap) if nkap > 1 else [2e-5])
+  sweep, M = _shard(sweep, M)
   dt = dt_days * DAY
   K = int(np.floor(2. * 360 * 86400 / dt))
   kappa = sweep['kappa'][:, None] + 0 * z[None, :]
@@ -121,7 +155,7 @@ def c3_twocol_so(M=262144, c=None, axes=None):
                     kappa=np.geomspace(1e-5, 8e-5, nk) if nk > 1 else [2e-5],
                     bs_north=np.linspace(0.002, 0.0045, nn) if nn > 1 else [0.004],
                     A_basin=np.linspace(6e13, 1.2e14, na) if na > 1 else [6e13])
-  assert sweep['tau'].size == M, (sweep['tau'].size, M)
+  sweep, M = _shard(sweep, M)
   kappa = sweep['kappa'][:, None] + 0 * z[None, :]
   A_b = sweep['A_basin'][:, None] + 0 * z[None, :]
   e300 = np.exp(z / 300.)
@@ -162,7 +196,7 @@ def twobasin(M=1, axes=None):
     sweep = lattice(tau=np.linspace(0.1, 0.2, n[0]) if n[0] > 1 else [0.16],
                     KGM=np.linspace(1400., 2200., n[1]) if n[1] > 1 else [1800.],
                     bs_north=np.linspace(0.0002, 0.0006, n[2]) if n[2] > 1 else [0.00036])
-  assert sweep['tau'].size == M
+  sweep, M = _shard(sweep, M)
   bs_north = sweep['bs_north']
   bbot = np.minimum(bAABW, bs_north)
   A_Atl, A_north, A_Pac = 7e13, 5.5e12, 1.7e14
@@ -225,7 +259,7 @@ def c4_jansen_nadeau(M=1, axes=None):
                     db=np.linspace(-0.004, 0.002, n[2]) if n[2] > 1 else [0.0],
                     B=np.linspace(3e3, 9e3, n[3]) if n[3] > 1 else [5.9e3],
                     KGM=np.linspace(750., 950., n[4]) if n[4] > 1 else [800.])
-  assert sweep['tau'].size == M
+  sweep, M = _shard(sweep, M)
   db = sweep['db']
   bs, bs_north, bminSO = 0.02 + db, -0.001 + db, 0.0 + db
   h, L = 50., 4e6
@@ -273,7 +307,7 @@ def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None, kapfac_max=2.):
                     kapfac=np.geomspace(0.5, kapfac_max, n[1]) if n[1] > 1 else [1.0],
                     KGM=np.linspace(500., 1500., n[2]) if n[2] > 1 else [1.0e3],
                     Ks=np.linspace(500., 900., n[3]) if n[3] > 1 else [1.0e3])
-  assert sweep['tau'].size == M
+  sweep, M = _shard(sweep, M)
   bs, bs_north, bminSO = 0.025, 0.0, 0.0
   h, L = 50., 2e7
   Bloss = 5.0e4 / L / 2e5

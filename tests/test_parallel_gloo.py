@@ -72,3 +72,25 @@ def test_sharded_ensemble_equals_single_process(tmp_path, world, M):
   ens.run(nsteps)
   assert np.array_equal(got['b'], ens.state()['b_basin'])
   assert np.array_equal(got['psi'], ens.diagnostics()['Psi_iso_b'])
+
+
+def test_sharded_spec_construction_equals_slice():
+  """configs.members(lo, hi) builds exactly the members [lo, hi) of the global lattice."""
+  from pymoc_b200 import configs
+  for build, M in ((configs.c2_column_so, 64), (configs.c3_twocol_so, 64), (configs.c4_jansen_nadeau, 32),
+                   (configs.twobasin, 8)):
+    whole = build(M)
+    lo, hi = M // 4 + 1, M - 3
+    with configs.members(lo, hi):
+      part = build(M)
+    assert part.M == hi - lo
+    for m in (0, (hi - lo) // 2, hi - lo - 1):
+      a, b = part.member_case(m), whole.member_case(lo + m)
+
+      def same(x, y):
+        if isinstance(x, dict):
+          return set(x) == set(y) and all(same(x[k], y[k]) for k in x)
+        if x is None or y is None:
+          return x is None and y is None
+        return np.array_equal(np.asarray(x), np.asarray(y))
+      assert same(a, b), (build.__name__, m)
