@@ -5,18 +5,11 @@
 #ifndef PM_LPL
 #error "compile with -DPM_LPL=<levels per lane>"
 #endif
-#ifndef PM_MINB_SMALL
-#define PM_MINB_SMALL 4
-#endif
+
 
 namespace pmk {
-// resident CTAs per SM the register allocation aims at.  Five (96 registers, 20 warps/SM) fit the
-// single-column topologies' shared memory, but measured slower on C2 (0.72 vs 0.76 of the roofline):
-// the spills of the tighter budget cost more than the extra warps hide.  -DPM_MINB_SMALL=5 to retry.
-constexpr int min_ctas(unsigned topo) { return (topo & (PMOC_HAS_NORTH | PMOC_HAS_ML | PMOC_SO_BVP)) ? 4 : PM_MINB_SMALL; }
-
 template <int LPL, unsigned TOPO>
-PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, min_ctas(TOPO)) k_model(RunArgs a) {
+PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
@@ -392,9 +385,23 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kWarpsPerBlock, min_ctas(TOPO)) k_model(Run
 template <int LPL>
 int launch_model(const RunArgs& ra, void* stream) {
   const unsigned t = ra.m.flags & (PMOC_HAS_NORTH | PMOC_HAS_TW | PMOC_ISO | PMOC_HAS_SO | PMOC_HAS_ML | PMOC_SO_BVP | PMOC_HAS_PAC);
-  const long long grid = blocks_for(ra.m.M);
-  const int block = 32 * kWarpsPerBlock;
-  const size_t smem = ra.sp.bytes(kWarpsPerBlock);
+  // Warps (= members) per CTA: the block-level tables are shared by a CTA's warps, so fewer, larger CTAs
+  // leave more shared memory for members; take the split with the most resident warps per SM, at most 16
+  // (128 registers per thread); four warps per CTA unless another split is strictly better.
+  auto resident = [&](int w) {
+    const size_t need = ra.sp.bytes(w) + 1024;  // + the per-CTA reservation
+    if (need > 228 * 1024) return 0;
+    int ctas = (int)((228 * 1024) / need);
+    if (ctas * w > 16) ctas = 16 / w;
+    return ctas * w;
+  };
+  int wpb = kWarpsPerBlock, best = resident(kWarpsPerBlock);  // four warps per CTA unless another split is better
+  for (int w = 1; w <= kMaxWarpsPerBlock; ++w)
+    if (resident(w) > best) { best = resident(w); wpb = w; }
+  if (best == 0) return fail(PMOC_EUNSUPPORTED, "model does not fit the shared memory of one SM");
+  const long long grid = (ra.m.M + wpb - 1) / wpb;
+  const int block = 32 * wpb;
+  const size_t smem = ra.sp.bytes(wpb);
 #define PM_CASE(T) \
   case (T): return launch(k_model<LPL, (T)>, grid, block, smem, stream, ra);
   switch (t) {
