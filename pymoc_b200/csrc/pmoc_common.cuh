@@ -46,6 +46,7 @@ struct SmemPlan {
   int off_tap;                                                      // per block, 4*nzp Psi_SO tapers
   int off_warp0, per_warp;                                          // per warp region
   int w_col[3];                                                     // column tables of basin / north / pac (3 or 4 nzp each)
+  int col_tables;                                                   // 0: folded coefficients are built from global memory
   int w_remap, w_psib, w_cnt, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
@@ -79,9 +80,15 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
   s.off_warp0 = o;
   int w = 0;
   const int colw = exact ? 4 : 3;  // arrays per column table
-  s.w_col[0] = w; w += colw * s.nzp;
-  if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += colw * s.nzp; }
-  if (flags & PMOC_HAS_PAC) { s.w_col[2] = w; w += colw * s.nzp; }
+  // The folded-step tables (dt*kappa, dt/A, dAk) are read once per diagnosis.  With several columns they would
+  // cost resident warps (16 KB per member instead of 12), so those topologies read the profiles from global
+  // memory (L2) instead; the single-column kernels are register-limited anyway and keep them.
+  s.col_tables = exact || !(flags & PMOC_HAS_NORTH);
+  if (s.col_tables) {
+    s.w_col[0] = w; w += colw * s.nzp;
+    if (flags & PMOC_HAS_NORTH) { s.w_col[1] = w; w += colw * s.nzp; }
+    if (flags & PMOC_HAS_PAC) { s.w_col[2] = w; w += colw * s.nzp; }
+  }
   if (exact) {
     // psib[nb] + the class counters are live only inside a refresh: they overlay the column tables,
     // which the kernel re-tabulates from global memory (L2) at the end of every refresh

@@ -162,6 +162,41 @@ PM_DEV void col_coeffs(double (&p)[LPL], double (&q)[LPL], const double (&wA)[LP
   }
 }
 
+// The same coefficients straight from the (host-sampled) global profiles, for topologies whose
+// per-member tables would cost resident warps: identical expressions, hence identical values.
+template <int LPL>
+PM_DEV void col_coeffs_global(double (&p)[LPL], double (&q)[LPL], const double (&wA)[LPL],
+                              const double* PM_RESTRICT kappa, const double* PM_RESTRICT dAk,
+                              const double* PM_RESTRICT Area, double dt, const GeoTab& G, int nz) {
+  double kdt[LPL], ra[LPL], dk[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {  // the loads first, so that they overlap
+    const int i = lev<LPL>(j);
+    const bool in = i >= 1 && i < nz - 1;
+    kdt[j] = in ? kappa[i] : 0.0;
+    ra[j] = in ? Area[i] : 1.0;
+    dk[j] = in ? dAk[i] : 0.0;
+  }
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j), s = lm(j);
+    double pj = 0.0, qj = 0.0;
+    if (i >= 1 && i < nz - 1) {
+      const double weff = wA[j] - dk[j];
+      const double rav = dt / ra[j];
+      const double kd = dt * kdt[j];
+      pj = kd * G.ruu[s];
+      qj = kd * G.rdd2[s];
+      if (weff < 0)
+        pj = pj - weff * (rav * G.rdu[s]);
+      else
+        qj = qj + weff * (rav * G.rdd[s]);
+    }
+    p[j] = pj;
+    q[j] = qj;
+  }
+}
+
 // One explicit step: 2 neighbour shuffles, LPL+1 subtractions, 2*LPL FMAs.
 template <int LPL>
 PM_DEV void col_step(double (&b)[LPL], const double (&p)[LPL], const double (&q)[LPL]) {

@@ -46,15 +46,17 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
   if (NORTH) col_load<LPL>(cn, M.north, m, nz);
   if (PAC) col_load<LPL>(cp, M.pac, m, nz);
   if (!ML) {
-    cb.tab = coltab_of(ws, sp, 0);
-    col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
-    if (NORTH) {
-      cn.tab = coltab_of(ws, sp, 1);
-      col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
-    }
-    if (PAC) {
-      cp.tab = coltab_of(ws, sp, 2);
-      col_retabulate<LPL>(cp, M.pac, m, G, nz, dt);
+    if (sp.col_tables) {
+      cb.tab = coltab_of(ws, sp, 0);
+      col_retabulate<LPL>(cb, M.basin, m, G, nz, dt);
+      if (NORTH) {
+        cn.tab = coltab_of(ws, sp, 1);
+        col_retabulate<LPL>(cn, M.north, m, G, nz, dt);
+      }
+      if (PAC) {
+        cp.tab = coltab_of(ws, sp, 2);
+        col_retabulate<LPL>(cp, M.pac, m, G, nz, dt);
+      }
     }
   } else {
     EG = exactgeo_of(sm, sp);
@@ -106,6 +108,15 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
     for (int e = 0; e < pm::kMLP; ++e) ml.bs[e] = ws[sp.w_bs + (pm::mlk(e) < ny ? pm::mlk(e) : ny - 1)];
   }
 
+  // folded stencil coefficients of one column from wA (tables in shared memory or the global profiles)
+  auto coeffs = [&](ColRegs<LPL>& c, const pmoc_column& d, const double(&wA)[LPL]) {
+    if (sp.col_tables) {
+      pm::col_coeffs<LPL>(c.p, c.q, wA, c.tab, G, nz);
+    } else {
+      const long long voff = (long long)c.var * nz;
+      pm::col_coeffs_global<LPL>(c.p, c.q, wA, vrow(d.kappa, m) + voff, vrow(d.dAk, m) + voff, vrow(d.Area, m), dt, G, nz);
+    }
+  };
   // Streamfunctions -> stencil coefficients of the columns (and what SO_ML needs).
   auto apply = [&](const double(&north_leg)[LPL], const double(&iso_n)[LPL], const double(&psi_so)[LPL],
                    const double(&zon_a)[LPL], const double(&zon_p)[LPL], const double(&psi_so2)[LPL]) {
@@ -113,7 +124,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
     if (PAC) {  // twobasin_NadeauJansen.py:104-106
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) wA[j] = (-zon_p[j] - psi_so2[j]) * 1e6;
-      pm::col_coeffs<LPL>(cp.p, cp.q, wA, cp.tab, G, nz);
+      coeffs(cp, M.pac, wA);
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) wA[j] = (north_leg[j] + zon_a[j] - psi_so[j]) * 1e6;
     } else {
@@ -123,14 +134,14 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
     if (ML)
       pm::col_nweff<LPL>(xb, wA, vrow(M.basin.dAk, m), nz, M.basin.nvar);
     else
-      pm::col_coeffs<LPL>(cb.p, cb.q, wA, cb.tab, G, nz);
+      coeffs(cb, M.basin, wA);
     if (NORTH) {
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) wA[j] = -iso_n[j] * 1e6;
       if (ML)
         pm::col_nweff<LPL>(xn, wA, vrow(M.north.dAk, m), nz, M.north.nvar);
       else
-        pm::col_coeffs<LPL>(cn.p, cn.q, wA, cn.tab, G, nz);
+        coeffs(cn, M.north, wA);
     }
     if (ML) {
       psi_so1 = pm::get_level<LPL>(psi_so, 1);
