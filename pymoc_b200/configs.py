@@ -116,7 +116,7 @@ def twocol(M=1):
   dt = 86400 * 30
   K = int(np.floor(2 * 360 * 86400 / dt))
   kap = 1e-5 + 3e-4 * np.exp(-z / 1000 - 4)
-  sweep = lattice(kapfac=np.linspace(0.5, 2.0, M)) if M > 1 else {}
+  sweep = lattice(kapfac=np.linspace(0.5, 1.25, M)) if M > 1 else {}  # above ~1.3 the explicit step is unstable
   kappa = kap if M == 1 else sweep['kapfac'][:, None] * kap[None, :]
   return ModelSpec(
       M=M, z=z, dt=dt, K=K, name='example_twocol', sweep=sweep,

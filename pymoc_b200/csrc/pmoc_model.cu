@@ -8,8 +8,18 @@
 
 
 namespace pmk {
+// Resident warps per SM the register allocation allows: 16 at 128 registers per thread.  The multi-column
+// 'post' topologies have shared memory for ~19 members per SM, but compiled for 20 warps (96 registers,
+// -DPM_WARPS_MULTI=20) they measured slower: C3 0.63 vs 0.66, two-basin 0.54 vs 0.56 of the roofline.
+#ifndef PM_WARPS_MULTI
+#define PM_WARPS_MULTI 16
+#endif
+constexpr int max_warps(unsigned topo) {
+  return ((topo & PMOC_HAS_NORTH) && !(topo & (PMOC_HAS_ML | PMOC_SO_BVP))) ? PM_WARPS_MULTI : 16;
+}
+
 template <int LPL, unsigned TOPO>
-PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * kMaxWarpsPerBlock, 1) k_model(RunArgs a) {
+PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
   constexpr bool NORTH = (TOPO & PMOC_HAS_NORTH) != 0, TW = (TOPO & PMOC_HAS_TW) != 0;
   constexpr bool ISO = (TOPO & PMOC_ISO) != 0, SO = (TOPO & PMOC_HAS_SO) != 0;
   constexpr bool ML = (TOPO & PMOC_HAS_ML) != 0;  // SO_ML + the loop order of run_JansenNadeau_2018.py
@@ -399,15 +409,16 @@ int launch_model(const RunArgs& ra, void* stream) {
   // Warps (= members) per CTA: the block-level tables are shared by a CTA's warps, so fewer, larger CTAs
   // leave more shared memory for members; take the split with the most resident warps per SM, at most 16
   // (128 registers per thread); four warps per CTA unless another split is strictly better.
+  const int cap = max_warps(t);
   auto resident = [&](int w) {
     const size_t need = ra.sp.bytes(w) + 1024;  // + the per-CTA reservation
     if (need > 228 * 1024) return 0;
     int ctas = (int)((228 * 1024) / need);
-    if (ctas * w > 16) ctas = 16 / w;
+    if (ctas * w > cap) ctas = cap / w;
     return ctas * w;
   };
   int wpb = kWarpsPerBlock, best = resident(kWarpsPerBlock);  // four warps per CTA unless another split is better
-  for (int w = 1; w <= kMaxWarpsPerBlock; ++w)
+  for (int w = 1; w <= cap; ++w)
     if (resident(w) > best) { best = resident(w); wpb = w; }
   if (best == 0) return fail(PMOC_EUNSUPPORTED, "model does not fit the shared memory of one SM");
   const long long grid = (ra.m.M + wpb - 1) / wpb;
