@@ -696,7 +696,7 @@ PM_DEV double interp_bgrid(double x, const BGrid& G, const double* psib_s) {
   const double fj = psib_s[j];
   if (xj == x) return fj;
   const double xj1 = G.at(j + 1), fj1 = psib_s[j + 1];
-  const double slope = qdiv(fj1 - fj, xj1 - xj);
+  const double slope = rt::div_normal(fj1 - fj, xj1 - xj);  // xj1 - xj: one grid step > 0
   double res = slope * (x - xj) + fj;
   if (res != res) {
     res = slope * (x - xj1) + fj1;
@@ -1129,7 +1129,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     if (BVP) {
       g = qdiv(P.KGM * z, dy) * P.L * P.toptap[s] * P.bottap[s];
     } else {
-      const double sl = qdiv(z, dy), ms = -P.smax;
+      const double sl = rt::div_normal(z, dy), ms = -P.smax;  // dy >= 0.1, |z| <= H: in range
       const double mx = (sl >= ms || sl != sl) ? sl : ms;
       g = P.KGM * mx * P.L * P.toptap[s] * P.bottap[s];
     }
