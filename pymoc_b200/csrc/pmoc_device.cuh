@@ -41,6 +41,16 @@ PM_DEV double qdiv(double a, double b) {
   return a / b;
 }
 
+// a / b without branches for a finite a and a finite b that is zero or normal, quotient in the normal range:
+// the in-range sequence, with the IEEE results of a zero divisor (+-inf, 0/0 = NaN) selected afterwards.
+// (An infinite operand -- a blown-up member -- gives NaN where IEEE gives 0 / inf.)
+PM_DEV double sdiv(double a, double b) {
+  const bool bz = b == 0.0;
+  const double q = rt::div_normal(a, bz ? 1.0 : b);
+  const double z = (a != a || a == 0.0) ? NAN : ((std::signbit(a) != std::signbit(b)) ? -INFINITY : INFINITY);
+  return bz ? z : q;
+}
+
 // registers <- natural-order global/shared array
 template <int LPL>
 PM_DEV void load_lev(double (&v)[LPL], const double* PM_RESTRICT g, int n, double pad) {
@@ -375,7 +385,7 @@ PM_DEV void tw_solve(double (&psi)[LPL], const double (&b1)[LPL], const double (
     if (i < nz - 1) {
       const double h = zs[i + 1] - zs[i];
       const double gm = gmid ? rf * gmid[i] : 0.5 * (gi + gi1);
-      t = h / 6. * (gi + 4. * gm + gi1);
+      t = div_const(h, 6., 1. / 6.) * (gi + 4. * gm + gi1);
     }
     T[j] = t;
     part[j] = run;
@@ -390,7 +400,7 @@ PM_DEV void tw_solve(double (&psi)[LPL], const double (&b1)[LPL], const double (
     double cell = 0.0;
     if (i < nz - 1) {
       const double h = zs[i + 1] - zs[i];
-      cell = h * (base1 + part[j]) + h * T[j] / 2. - h * h / 12. * (gi1 - gi);
+      cell = h * (base1 + part[j]) + h * T[j] / 2. - div_const(h * h, 12., 1. / 12.) * (gi1 - gi);
     }
     part[j] = run;
     run = run + cell;
@@ -627,8 +637,8 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
         b2_s[i] = m2[j];
         S1_s[i] = s1[j] + e1;
         S2_s[i] = s2[j] + e2;
-        w1_s[i] = (cell && !from2) ? u[j] / ((last ? m1n : m1[jn]) - m1[j]) : 0.0;
-        w2_s[i] = (cell && from2) ? u[j] / ((last ? m2n : m2[jn]) - m2[j]) : 0.0;
+        w1_s[i] = (cell && !from2) ? sdiv(u[j], (last ? m1n : m1[jn]) - m1[j]) : 0.0;
+        w2_s[i] = (cell && from2) ? sdiv(u[j], (last ? m2n : m2[jn]) - m2[j]) : 0.0;
       }
     }
     rt::syncwarp();
@@ -729,7 +739,7 @@ PM_DEV double interp1(double x, const double* xp, const double* fp, int n) {
   const int j = search_le(xp, n, x);
   if (j == n - 1) return fp[j];
   if (xp[j] == x) return fp[j];
-  const double slope = qdiv(fp[j + 1] - fp[j], xp[j + 1] - xp[j]);
+  const double slope = sdiv(fp[j + 1] - fp[j], xp[j + 1] - xp[j]);
   double res = slope * (x - xp[j]) + fp[j];
   if (res != res) {
     res = slope * (x - xp[j + 1]) + fp[j + 1];
@@ -1215,7 +1225,7 @@ PM_DEV double interp_at(double x, XP xp, const double* fp, int n, int k) {
   if (k == n) return fp[n - 1];
   if (k == n - 1) return fp[k];
   if (xp[k] == x) return fp[k];
-  const double slope = qdiv(fp[k + 1] - fp[k], xp[k + 1] - xp[k]);
+  const double slope = sdiv(fp[k + 1] - fp[k], xp[k + 1] - xp[k]);
   double res = slope * (x - xp[k]) + fp[k];
   if (res != res) {
     res = slope * (x - xp[k + 1]) + fp[k + 1];
