@@ -193,7 +193,7 @@ PM_DEV void col_coeffs_global(double (&p)[LPL], double (&q)[LPL], const double (
     double pj = 0.0, qj = 0.0;
     if (i >= 1 && i < nz - 1) {
       const double weff = wA[j] - dk[j];
-      const double rav = dt / ra[j];
+      const double rav = rt::div_normal(dt, ra[j]);  // Area: finite, normal
       const double kd = dt * kdt[j];
       pj = kd * G.ruu[s];
       qj = kd * G.rdd2[s];
@@ -568,7 +568,7 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
         const double bot = from2 ? b2[j] : b1[j];
         const double top = from2 ? up2[j] : up1[j];
         ctop[pos] = top;
-        crinv[pos] = 1.0 / (top - bot);
+        crinv[pos] = sdiv(1.0, top - bot);
         cu[pos] = u[j];
         ++pos;
       }
@@ -840,6 +840,7 @@ PM_DEV double mean100(double tau) {
 
 struct SoPar {
   double tau_ave, f, rho, L, KGM, smax;
+  double pre0;  // tau_ave / f / rho * L (psi_SO.py:243, left to right), constant between launches
   const double *sill, *ektap, *toptap, *bottap;  // taper profiles, lane-major (shared memory)
   const double* tau_y;                           // tau on the y grid (shared memory) or nullptr for a float tau
   double c;                                      // F2010 phase speed (BVP branch only)
@@ -880,7 +881,7 @@ PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int n
   bool down = false;
   for (int k = rt::lane(); k < ny - 1; k += 32) {
     const double db = bs[k + 1] - bs[k];
-    sinv[k] = (ygrid[k + 1] - ygrid[k]) / db;
+    sinv[k] = sdiv(ygrid[k + 1] - ygrid[k], db);
     if (k >= s.south && db < 0) down = true;
   }
   s.mono = rt::ballot(down) == 0;
@@ -1091,7 +1092,7 @@ template <int LPL, bool BVP = false>
 PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], double (&ysv)[LPL],
                      const double (&b)[LPL], const double* ygrid, const double* bs, const double* sinv, int ny,
                      const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status) {
-  const double pre0 = P.tau_ave / P.f / P.rho * P.L;
+  const double pre0 = P.pre0;
   const double c6 = 1e6, r6 = 1.0 / 1e6;
   if (S.mono && S.south < ny - 1) {
     outcrop_monotone_all<LPL>(ysv, b, ygrid, bs, sinv, ny, S);

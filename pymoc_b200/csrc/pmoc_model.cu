@@ -104,8 +104,12 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
     rt::syncwarp();
     if (!ML) surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);  // bs(y) is fixed without a mixed layer
   }
+  if (SO) so.pre0 = so.tau_ave / so.f / so.rho * so.L;
   pm::SoPar so2 = so;  // the pac sector's Psi_SO differs in its zonal length only (twobasin_NadeauJansen.py:76-81)
-  if (PAC) so2.L = vat(M.so2_L, m);
+  if (PAC) {
+    so2.L = vat(M.so2_L, m);
+    so2.pre0 = so2.tau_ave / so2.f / so2.rho * so2.L;
+  }
   unsigned status = 0;
   pm::MlState ml{};
   double* const bb_s = ws + (ML ? sp.w_bb : 0);

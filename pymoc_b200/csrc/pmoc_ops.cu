@@ -135,6 +135,7 @@ PM_GLOBAL void k_so(SoArgs a) {
   }
   so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
   so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
+  so.pre0 = so.tau_ave / so.f / so.rho * so.L;
   so.sill = tap; so.ektap = tap + a.nzp; so.toptap = tap + 2 * a.nzp; so.bottap = tap + 3 * a.nzp;
   so.c = BVP ? vat(M.so_c, m) : 0.0;
   so.with_Ek = M.so_bvp_with_Ek;
