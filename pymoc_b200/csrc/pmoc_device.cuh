@@ -1442,10 +1442,7 @@ template <class XP>
 PM_DEV void ml_step(MlState& S, XP bb_s, const double* pm_s, int nz, bool sorted, double* bs_s, double dt,
                     unsigned* status) {
   const int ny = S.ny, Ln = rt::lane();
-  PM_UNROLL
-  for (int e = 0; e < kMLP; ++e)
-    if (mlk(e) < ny) bs_s[mlk(e)] = S.bs[e];
-  rt::syncwarp();
+  (void)bs_s;
   double ps[kMLP] = {0., 0.};
   if (sorted) {
     PM_UNROLL
