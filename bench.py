@@ -279,10 +279,10 @@ def gpu_arm(args):
     tt = torch.tensor([dt_e2e], dtype=torch.float64, device='cuda')
     if world > 1:
       dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    state_bytes = sum(b.numel() * b.element_size() for k, b in hens._bufs.items()
-                      if k.startswith(('b_', 'bbot', 'var', 'bs_ml', 'status')))
+    h2d, d2h = ctypes.c_uint64(), ctypes.c_uint64()
+    lib.pmoc_host_last_bytes(ctypes.byref(h2d), ctypes.byref(d2h))  # what the last call actually copied
     e2e = {'value': M * nt * args.e2e_steps / float(tt.item()), 'unit': 'member-timesteps/s',
-           'h2d_bytes_per_step': int(hb.bytes_in + hb.bytes_out), 'd2h_bytes_per_step': int(hb.bytes_out + state_bytes),
+           'h2d_bytes_per_step': int(h2d.value), 'd2h_bytes_per_step': int(d2h.value),
            'steps': args.e2e_steps, 'api': 'pmoc_model_run_host (pinned host buffers)'}
     hfin = hens.state()['b_basin']
     assert (~np.isfinite(hfin).all(axis=1)).sum() <= 1e-3 * hens.M, 'non-finite members in the host-buffer run'

@@ -165,6 +165,8 @@ int pmoc_model_run(const pmoc_model* m, int64_t it0, int64_t nsteps, void* strea
  * buffers are allocated, inputs copied in, the fused kernel run, and state + diagnostics
  * copied back before returning (synchronous).  This is the call a non-torch consumer binds. */
 int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nsteps);
+/* bytes the last pmoc_model_run_host of this thread copied host->device / device->host */
+void pmoc_host_last_bytes(uint64_t* h2d, uint64_t* d2h);
 
 /* ---- per-module entry points (the reference's method surface), batched over M ----------- */
 

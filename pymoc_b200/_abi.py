@@ -44,7 +44,7 @@ class Model(C.Structure):
 
 
 EXPORTS = ('pmoc_abi_version', 'pmoc_last_error', 'pmoc_device_info', 'pmoc_model_scratch_bytes', 'pmoc_model_diagnose', 'pmoc_model_run',
-           'pmoc_model_run_host', 'pmoc_column_timestep', 'pmoc_thermwind_solve', 'pmoc_thermwind_psib',
+           'pmoc_model_run_host', 'pmoc_host_last_bytes', 'pmoc_column_timestep', 'pmoc_thermwind_solve', 'pmoc_thermwind_psib',
            'pmoc_so_solve', 'pmoc_ml_timestep', 'pmoc_fp64_peak')
 
 
@@ -60,6 +60,8 @@ def declare(lib):
   lib.pmoc_model_diagnose.argtypes = [P(Model), C.c_void_p]
   lib.pmoc_model_run.argtypes = [P(Model), C.c_int64, C.c_int64, C.c_void_p]
   lib.pmoc_model_run_host.argtypes = [P(Model), C.c_int64, C.c_int64]
+  lib.pmoc_host_last_bytes.argtypes = [P(C.c_uint64), P(C.c_uint64)]
+  lib.pmoc_host_last_bytes.restype = None
   lib.pmoc_column_timestep.argtypes = [C.c_int64, C.c_int32, C.c_void_p, P(Column), Vec, Vec, Vec, C.c_double,
                                        C.c_uint32, C.c_void_p]
   lib.pmoc_thermwind_solve.argtypes = [C.c_int64, C.c_int32, C.c_void_p, Vec, Vec, Vec, Vec, C.c_void_p, C.c_void_p]
@@ -70,7 +72,7 @@ def declare(lib):
   lib.pmoc_ml_timestep.argtypes = [P(Model), Vec, Vec, C.c_double, C.c_void_p, C.c_void_p]
   lib.pmoc_fp64_peak.argtypes = [P(C.c_double), P(C.c_double), C.c_void_p]
   for name in EXPORTS:
-    if name not in ('pmoc_last_error', 'pmoc_model_scratch_bytes'):
+    if name not in ('pmoc_last_error', 'pmoc_model_scratch_bytes', 'pmoc_host_last_bytes'):
       getattr(lib, name).restype = C.c_int
   lib.pmoc_model_scratch_bytes.restype = C.c_uint64
   if lib.pmoc_abi_version() != ABI_VERSION:

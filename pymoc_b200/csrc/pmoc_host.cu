@@ -3,6 +3,13 @@
 
 #include <vector>
 
+static thread_local unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+
+extern "C" void pmoc_host_last_bytes(uint64_t* h2d, uint64_t* d2h) {
+  if (h2d) *h2d = g_h2d_bytes;
+  if (d2h) *d2h = g_d2h_bytes;
+}
+
 #ifndef PMOC_EMU
 namespace {
 
@@ -10,6 +17,9 @@ namespace {
 // call over blocks of members: block c's host->device copies, kernel and device->host copies are queued on
 // stream c % kStreams, so the copies of one block overlap the kernel of another (members are independent).
 constexpr int kStreams = 3;
+#ifndef PMOC_HOST_BLOCK_MEMBERS
+#define PMOC_HOST_BLOCK_MEMBERS 4096  // 16 blocks for the 65,536-member bench: fill/drain of the pipeline ~6 % of the copies
+#endif
 
 struct Mirror {
   struct Field {
@@ -51,8 +61,8 @@ struct Mirror {
   template <class T>
   void shared(const T** dp, size_t n) { add(dp, *dp, 0, n * sizeof(T), true, false); }
   template <class T>
-  void state(T** dp, long long M, size_t len, bool upload) {  // per-member output, optionally also input
-    add(dp, *dp, len * sizeof(T), (size_t)M * len * sizeof(T), upload, true);
+  void state(T** dp, long long M, size_t len, bool upload, bool download = true) {  // per-member in/out array
+    add(dp, *dp, len * sizeof(T), (size_t)M * len * sizeof(T), upload, download);
   }
   void column(pmoc_column* c, long long M, int nz) {
     state(&c->b, M, nz, true);
@@ -67,8 +77,10 @@ struct Mirror {
   }
   void upload_shared() {
     for (auto& f : fields)
-      if (!f.per_member && f.in && err == cudaSuccess)
+      if (!f.per_member && f.in && err == cudaSuccess) {
         err = cudaMemcpyAsync(f.dev, f.host, f.bytes, cudaMemcpyHostToDevice, s[0]);
+        g_h2d_bytes += f.bytes;
+      }
     if (err == cudaSuccess) err = cudaEventRecord(shared_ready, s[0]);
   }
   // members [m0, m0+n) in, on stream st; the last member of an input vector may be shorter than its stride
@@ -80,6 +92,7 @@ struct Mirror {
       if (off + len > f.bytes) len = f.bytes - off;
       err = f.in ? cudaMemcpyAsync(f.dev + off, f.host + off, len, cudaMemcpyHostToDevice, st)
                  : cudaMemsetAsync(f.dev + off, 0, len, st);
+      if (f.in) g_h2d_bytes += len;
     }
   }
   void download_block(long long m0, long long n, cudaStream_t st) {
@@ -87,6 +100,7 @@ struct Mirror {
       if (!f.per_member || !f.out || err != cudaSuccess) continue;
       const size_t off = (size_t)m0 * f.per_member;
       err = cudaMemcpyAsync(f.host + off, f.dev + off, (size_t)n * f.per_member, cudaMemcpyDeviceToHost, st);
+      g_d2h_bytes += (size_t)n * f.per_member;
     }
   }
   // the device model restricted to members [m0, m0+n)
@@ -108,6 +122,7 @@ struct Mirror {
 
 extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nsteps) {
   if (!m) return fail(PMOC_EINVAL, "model is NULL");
+  g_h2d_bytes = g_d2h_bytes = 0;
 #ifdef PMOC_EMU
   if (it0 == 0 && !(m->flags & PMOC_ORDER_JN))
     if (int rc = pmoc_model_diagnose(m, nullptr)) return rc;
@@ -131,7 +146,13 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
   mr.h = m;
   mr.d = *m;
   pmoc_model& d = mr.d;
-  const bool carry = it0 > 0;  // streamfunctions diagnosed by an earlier call are inputs
+  // Diagnostics: the kernel rewrites all of them at the last iteration with ii % K == 0 of the launch (and the
+  // pre-loop diagnosis of an order-'post' model at it0 == 0 does); without such an iteration they are left
+  // alone on both sides.  Only the streamfunctions the step loop carries from an earlier launch are inputs.
+  const long long K = m->K > 0 ? m->K : 1;
+  const bool jn = (f & PMOC_ORDER_JN) != 0;
+  const bool rewritten = (!jn && it0 == 0) || (nsteps > 0 && ((it0 + nsteps - 1) / K) * K >= it0);
+  const bool carry = jn ? (it0 % K != 0) : (it0 > 0);
   mr.shared(&d.z, nz);
   mr.shared(&d.y, ny);
   mr.column(&d.basin, M, nz);
@@ -140,14 +161,14 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
     mr.column(&d.pac, M, nz);
     mr.vec(&d.zoc_f, M, 1);
     mr.vec(&d.so2_L, M, 1);
-    mr.state(&d.Psi_zoc, M, nz, carry);
-    mr.state(&d.Psi_zon_a, M, nz, carry);
-    mr.state(&d.Psi_zon_p, M, nz, carry);
-    mr.state(&d.psib2, M, nb, carry);
-    mr.state(&d.bgrid2, M, nb, carry);
-    mr.state(&d.Psi_so2, M, nz, carry);
-    mr.state(&d.Psi_Ek2, M, nz, carry);
-    mr.state(&d.Psi_GM2, M, nz, carry);
+    mr.state(&d.Psi_zoc, M, nz, false, rewritten);
+    mr.state(&d.Psi_zon_a, M, nz, carry, rewritten);
+    mr.state(&d.Psi_zon_p, M, nz, carry, rewritten);
+    mr.state(&d.psib2, M, nb, false, rewritten);
+    mr.state(&d.bgrid2, M, nb, false, rewritten);
+    mr.state(&d.Psi_so2, M, nz, carry, rewritten);
+    mr.state(&d.Psi_Ek2, M, nz, false, rewritten);
+    mr.state(&d.Psi_GM2, M, nz, false, rewritten);
   }
   mr.vec(&d.tw_f, M, 1);
   mr.vec(&d.tw_b2, M, nz);
@@ -171,20 +192,20 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
   mr.vec(&d.ml_surflux, M, ny);
   mr.vec(&d.ml_rest_mask, M, ny);
   mr.vec(&d.ml_b_rest, M, ny);
-  mr.state(&d.Psi_tw, M, nz, carry);
-  mr.state(&d.Psi_iso_b, M, nz, carry);
-  mr.state(&d.Psi_iso_n, M, nz, carry);
-  mr.state(&d.psib, M, nb, carry);
-  mr.state(&d.bgrid, M, nb, carry);
-  mr.state(&d.Psi_so, M, nz, carry);
-  mr.state(&d.Psi_Ek, M, nz, carry);
-  mr.state(&d.Psi_GM, M, nz, carry);
-  mr.state(&d.ml_Psi_s, M, ny, carry);
+  mr.state(&d.Psi_tw, M, nz, carry && !(f & PMOC_ISO), rewritten);
+  mr.state(&d.Psi_iso_b, M, nz, carry, rewritten);
+  mr.state(&d.Psi_iso_n, M, nz, carry, rewritten);
+  mr.state(&d.psib, M, nb, false, rewritten);
+  mr.state(&d.bgrid, M, nb, false, rewritten);
+  mr.state(&d.Psi_so, M, nz, carry, rewritten);
+  mr.state(&d.Psi_Ek, M, nz, false, rewritten);
+  mr.state(&d.Psi_GM, M, nz, false, rewritten);
+  mr.state(&d.ml_Psi_s, M, ny, false, nsteps > 0);
   mr.state(&d.status, M, 1, true);
   // blocks of members: enough of them to overlap copies with kernels, each large enough to fill the GPU
-  long long nblk = M / 8192;
+  long long nblk = M / PMOC_HOST_BLOCK_MEMBERS;
   if (nblk < 1) nblk = 1;
-  if (nblk > 16) nblk = 16;
+  if (nblk > 32) nblk = 32;
   const long long per = (M + nblk - 1) / nblk;
   void* scratch[kStreams] = {};
   d.scratch = nullptr;

@@ -19,7 +19,7 @@ def lib():
 def test_header_symbols_exported(lib):
   from pymoc_b200 import _abi
   header = open(os.path.join(ROOT, 'include', 'pymoc_b200.h')).read()
-  declared = set(re.findall(r'^(?:int|uint64_t|const char\*)\s+(pmoc_[a-z0-9_]+)\s*\(', header, flags=re.M))
+  declared = set(re.findall(r'^(?:int|void|uint64_t|const char\*)\s+(pmoc_[a-z0-9_]+)\s*\(', header, flags=re.M))
   assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
   for name in declared:
     assert hasattr(lib, name), name
