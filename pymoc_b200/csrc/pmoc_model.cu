@@ -2,6 +2,8 @@
 // unit (compile with -DPM_LPL=<2..8>).
 #include "pmoc_common.cuh"
 
+#include <cstdlib>
+
 #ifndef PM_LPL
 #error "compile with -DPM_LPL=<levels per lane>"
 #endif
@@ -425,6 +427,10 @@ int launch_model(const RunArgs& ra, void* stream) {
   for (int w = 1; w <= cap; ++w)
     if (resident(w) > best) { best = resident(w); wpb = w; }
   if (best == 0) return fail(PMOC_EUNSUPPORTED, "model does not fit the shared memory of one SM");
+  if (const char* e = std::getenv("PMOC_WPB")) {  // tuning knob: force the warps per CTA
+    const int w = std::atoi(e);
+    if (w >= 1 && w <= cap && resident(w) > 0) wpb = w;
+  }
   const long long grid = (ra.m.M + wpb - 1) / wpb;
   const int block = 32 * wpb;
   const size_t smem = ra.sp.bytes(wpb);

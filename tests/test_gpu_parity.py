@@ -96,7 +96,9 @@ def test_host_buffer_entry_point(cuda):
   # 16 members: one block; 32,768 members: four blocks pipelined over three streams
   for spec, keys in ((configs.c3_twocol_so(16, axes=(2, 2, 2, 2)), ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib')),
                      (configs.c2_column_so(32768), ('Psi_so', 'Psi_Ek', 'Psi_GM')),
-                     (configs.c4_jansen_nadeau(16384), ('Psi_iso_b', 'Psi_so', 'Psi_s', 'bbot_basin'))):
+                     (configs.c4_jansen_nadeau(16384), ('Psi_iso_b', 'Psi_so', 'Psi_s', 'bbot_basin')),
+                     # block-per-member kernels: the library allocates their scratch per stream (two blocks)
+                     (configs.c5_single_global_basin(8192, nz=320, dt_days=1., kapfac_max=1.), ('Psi_iso_b', 'Psi_so'))):
     dev = Ensemble(spec, backend=cuda)
     dev.run(30)
     host = Ensemble(spec, backend=HostBuffers(cuda.lib))
