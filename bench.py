@@ -77,12 +77,12 @@ def algorithmic_flops(spec):
 
 
 # DRAM bytes (read + write) of one fused-kernel launch, from the committed `ncu --set full` captures
-# (profiles/r1z_full_summary.txt).  State and parameters are read once and state + diagnostics written once
+# (profiles/r1final_full_summary.txt).  State and parameters are read once and state + diagnostics written once
 # per launch whatever the number of steps, so the 720/240-step captures stand for the bench's launches.
 NCU_TRAFFIC = {  # workload -> (members in the capture, bytes)
-    'C2': (65536, 420.9e6 + 366.5e6),
-    'C3': (32768, 232.3e6 + 387.6e6),
-    'C4': (32768, 258.4e6 + 482.8e6),
+    'C2': (65536, 421.1e6 + 362.5e6),
+    'C3': (32768, 232.2e6 + 386.6e6),
+    'C4': (32768, 257.4e6 + 478.5e6),
 }
 
 
@@ -310,7 +310,7 @@ def gpu_arm(args):
                      'frac': achieved / peak.value,
                      'traffic': (NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
                                  if args.workload in NCU_TRAFFIC else None),
-                     'traffic_source': 'bytes per launch (dram read + write), profiles/r1z_full_summary.txt',
+                     'traffic_source': 'bytes per launch (dram read + write), profiles/r1final_full_summary.txt',
                      'hbm_check': (None if args.workload not in NCU_TRAFFIC else {
                          'achieved_GBs': NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
                                          / (ms_per_step * 1e-3) / 1e9,
