@@ -689,30 +689,31 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
 
 // np.interp(x, bgrid, psib) (numpy/_core/src/multiarray/compiled_base.c: arr_interp) on the
 // implicit uniform grid: index by division, then corrected against the actual grid values.
+// Written without early exits: the index comes from one multiply-corrected divide (off by at most one
+// from the search's answer: the rounding of r and of the grid nodes is ~1e-13 of a grid step), two
+// predicated single-step corrections against the actual node values, then both nodes are loaded, the
+// segment evaluated and the special cases selected -- so that the interpolations of a lane overlap.
 PM_DEV double interp_bgrid(double x, const BGrid& G, const double* psib_s) {
-  if (x != x) return x;
   const int nb = G.nb;
-  if (x > G.hi) return psib_s[nb - 1];
-  if (x < G.lo) return psib_s[0];
-  int j = nb - 1;
-  if (G.step > 0.) {
-    const double r = div_const(x - G.lo, G.step, G.rstep);
-    j = r < (double)(nb - 1) ? (int)r : nb - 1;
-    while (j < nb - 1 && G.at(j + 1) <= x) ++j;
-    while (j > 0 && G.at(j) > x) --j;
-  }
-  if (j == nb - 1) return psib_s[j];
-  const double xj = G.at(j);
-  const double fj = psib_s[j];
-  if (xj == x) return fj;
-  const double xj1 = G.at(j + 1), fj1 = psib_s[j + 1];
-  const double slope = rt::div_normal(fj1 - fj, xj1 - xj);  // xj1 - xj: one grid step > 0
+  const bool flat = !(G.step > 0.);  // hi == lo (or NaN): every query sits on the last node
+  const double r = div_const(x - G.lo, flat ? 1.0 : G.step, flat ? 1.0 : G.rstep);
+  int j = (r >= 0.0 && r < (double)(nb - 1)) ? (int)r : (r >= 0.0 ? nb - 1 : 0);  // (NaN -> 0, unused)
+  if (j < nb - 1 && G.at(j + 1) <= x) ++j;
+  if (j > 0 && G.at(j) > x) --j;
+  if (flat) j = nb - 1;
+  const int jj = j < nb - 1 ? j : nb - 2;
+  const double xj = G.at(jj), xj1 = G.at(jj + 1), fj = psib_s[jj], fj1 = psib_s[jj + 1];
+  const double slope = rt::div_normal(fj1 - fj, flat ? 1.0 : xj1 - xj);  // xj1 - xj: one grid step > 0
   double res = slope * (x - xj) + fj;
-  if (res != res) {
+  if (res != res) {  // arr_interp's fall-backs for a NaN product (an infinite slope times zero)
     res = slope * (x - xj1) + fj1;
     if (res != res && fj == fj1) res = fj;
   }
-  return res;
+  if (xj == x) res = fj;
+  if (j == nb - 1) res = fj1;
+  if (x < G.lo) res = psib_s[0];
+  if (x > G.hi) res = psib_s[nb - 1];
+  return x != x ? x : res;
 }
 
 // ===================================================================== Psi_SO
