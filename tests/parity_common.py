@@ -71,3 +71,43 @@ def diag_and_pickup_files(backend, tmpdir):
   ens.run(24)
   for k, v in ens.state().items():
     assert np.array_equal(v, again.state()[k]), k
+
+
+def edge_sizes(backend, wide=True):
+  """Sizes at the dispatch boundaries of the kernels against the live oracle: levels per lane 2..8 (nz up to
+  256) with member counts that do not fill a CTA, the smallest grids, and the block-per-member kernels at
+  the boundaries of their levels-per-thread variants."""
+  import warnings
+
+  from oracle import pymoc_oracle as O
+  from pymoc_b200 import configs
+  warnings.filterwarnings('ignore')
+  worst = 0.0
+
+  def check(spec, nsteps, members, keys):
+    nonlocal worst
+    ens = Ensemble(spec, backend=backend)
+    ens.run(nsteps)
+    got = {**ens.state(), **ens.diagnostics()}
+    for m in members:
+      want = O.run_coupled(spec.member_case(m), nsteps, O.REFERENCE)
+      for key in keys:
+        err = relmax(got[key][m], want[key])
+        worst = max(worst, err)
+        assert err < TOL, (spec.name, spec.nz, m, key, err)
+
+  # column + Psi_SO: every levels-per-lane variant, 3 members (a partly filled CTA), smallest channel grid
+  for nz, ny in ((5, 3), (33, 40), (64, 7), (65, 40), (129, 40), (255, 40), (256, 64)):
+    with configs.members(0, 3):
+      spec = configs.c2_column_so(4, nz=nz, ny=ny, dt_days=0.5)
+    check(spec, 2 * spec.K + 3 if spec.K < 40 else 75, (0, 2), ('b_basin', 'Psi_so', 'Psi_Ek', 'Psi_GM'))
+  # 'jn' order at the warp kernels' largest grid and at a tiny one
+  for nz, dt_days in ((256, 2.), (12, 30.)):
+    with configs.members(1, 4):
+      spec = configs.c5_single_global_basin(4, nz=nz, dt_days=dt_days, axes=(2, 2, 1, 1), kapfac_max=1.)
+    check(spec, 30, (0, 2), ('b_basin', 'b_north', 'bs_ml', 'Psi_iso_b', 'Psi_so'))
+  if wide:  # block-per-member kernels: first size, boundaries of the 4 / 8 / 16 levels-per-thread variants
+    for nz, dt_days in ((257, 2.), (1024, 0.1), (1025, 0.1), (2049, 0.02)):
+      spec = configs.c5_single_global_basin(1, nz=nz, dt_days=dt_days)
+      check(spec, 25, (0,), ('b_basin', 'b_north', 'bs_ml', 'Psi_iso_b', 'Psi_so'))
+  return worst

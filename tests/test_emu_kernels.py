@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from emu.emu_backend import EmuBackend
-from parity_common import diag_and_pickup_files, run_against_golden
+from parity_common import diag_and_pickup_files, edge_sizes, run_against_golden
 
 
 @pytest.fixture(scope='module')
@@ -54,3 +54,7 @@ def test_jn_split_launches_bitwise(emu):
     assert np.array_equal(v, b.state()[k], equal_nan=True), k
   for k in ('Psi_iso_b', 'Psi_so', 'bbot_basin', 'bbot_north'):
     assert np.array_equal(a.diagnostics()[k], b.diagnostics()[k], equal_nan=True), k
+
+
+def test_edge_sizes_vs_live_oracle(emu):
+  edge_sizes(emu, wide=True)

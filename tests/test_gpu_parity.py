@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from helpers import relmax
-from parity_common import TOL, diag_and_pickup_files, run_against_golden
+from parity_common import TOL, diag_and_pickup_files, edge_sizes, run_against_golden
 
 pytestmark = pytest.mark.gpu
 warnings.filterwarnings('ignore', category=RuntimeWarning)
@@ -166,3 +166,7 @@ def test_jn_and_wide_split_launches_bitwise(cuda):
     da, db = a.diagnostics(), b.diagnostics()
     for k in ('Psi_iso_b', 'Psi_iso_n', 'Psi_so', 'bbot_basin', 'bbot_north'):
       assert np.array_equal(da[k], db[k], equal_nan=True), (spec.name, k)
+
+
+def test_edge_sizes_vs_live_oracle(cuda):
+  print('edge sizes: worst relative error %.2e' % edge_sizes(cuda, wide=True))
