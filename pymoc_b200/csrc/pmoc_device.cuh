@@ -872,13 +872,24 @@ PM_DEV void taper_fill(double* dst, const double* PM_RESTRICT sill, const double
 // north of it, and the inverse segment slopes.  Warp-cooperative; redone only when bs changes.
 PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int ny) {
   SoSurf s;
-  s.mn = bs[0];
-  s.south = 0;
-  for (int k = 1; k < ny; ++k)
-    if (bs[k] < s.mn) {
-      s.mn = bs[k];
-      s.south = k;
+  {  // mn, south = first occurrence of the minimum, as the scan `if (bs[k] < mn)` from k = 0 finds it (a NaN
+     // never wins unless it is bs[0]); lanes take k = lane, lane + 32, ..., then a warp arg-min
+    double v = INFINITY;
+    int idx = 0x7fffffff;
+    for (int k = rt::lane(); k < ny; k += 32) {
+      const double x = bs[k];
+      if (x < v) { v = x; idx = k; }
     }
+    for (int msk = 16; msk > 0; msk >>= 1) {
+      const double ov = rt::shfl_xor(v, msk);
+      const int oi = rt::shfl_i(idx, rt::lane() ^ msk);
+      if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+    const double b0 = bs[0];
+    const bool first = b0 != b0 || idx == 0x7fffffff;  // bs[0] is NaN, or nothing is below +inf
+    s.mn = first ? b0 : v;
+    s.south = first ? 0 : idx;
+  }
   bool down = false;
   for (int k = rt::lane(); k < ny - 1; k += 32) {
     const double db = bs[k + 1] - bs[k];
