@@ -433,8 +433,9 @@ PM_DEV int bgrid_count_le(const BGrid& G, double v) {
   if (!(G.step > 0.)) return v >= G.lo ? nb : 0;
   const double r = div_const(v - G.lo, G.step, G.rstep);
   int p = r < (double)(nb - 1) ? (int)r + 1 : nb;
-  while (p < nb && G.at(p) <= v) ++p;
-  while (p > 0 && G.at(p - 1) > v) --p;
+  // one correction each way suffices (see interp_bgrid): the rounding of r and of the nodes is ~1e-13 steps
+  if (p < nb && G.at(p) <= v) ++p;
+  if (p > 0 && G.at(p - 1) > v) --p;
   return p;
 }
 
