@@ -16,8 +16,16 @@ namespace pmk {
 #ifndef PM_WARPS_MULTI
 #define PM_WARPS_MULTI 16
 #endif
+// The 'jn' kernels (SO_ML, bit-faithful column step) carry more live state: compiled for 12 resident warps
+// (168 registers) they spill a quarter of what they spill at 128, and with shared memory for at most 15
+// members per SM little occupancy is lost.  Measured on C4: 16 warps/128 regs 0.236 of the roofline,
+// 12/168 0.247, 10/168 0.254, 8/250 0.206; on C5 (nz = 46): 0.089, 0.093, 0.088, 0.079.
+#ifndef PM_WARPS_JN
+#define PM_WARPS_JN 12
+#endif
 constexpr int max_warps(unsigned topo) {
-  return ((topo & PMOC_HAS_NORTH) && !(topo & (PMOC_HAS_ML | PMOC_SO_BVP))) ? PM_WARPS_MULTI : 16;
+  return (topo & PMOC_HAS_ML) ? PM_WARPS_JN
+                              : (((topo & PMOC_HAS_NORTH) && !(topo & PMOC_SO_BVP)) ? PM_WARPS_MULTI : 16);
 }
 
 template <int LPL, unsigned TOPO>
