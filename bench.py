@@ -306,7 +306,10 @@ def gpu_arm(args):
                    'l2': 'inputs (state + per-member parameters, %.0f MB per GPU) larger than the 126 MB L2'
                          % (ens.M * spec.nz * 8 * 3 / 1e6),
                    'parallelism': 'ensemble members sharded over %d GPU(s), no collective in the loop' % world},
-        'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
+        'roofline': {'bound': 'fp64',
+                     'bound_note': 'FP64 pipe (DFMA): the state stays on chip across the fused steps, BASELINE.json asks '
+                                   'for "% of FP64/HBM roofline"; hbm_check shows the HBM side',
+                     'achieved': achieved, 'peak': peak.value, 'unit': 'TFLOP/s',
                      'frac': achieved / peak.value,
                      'traffic': (NCU_TRAFFIC[args.workload][1] * m_local / NCU_TRAFFIC[args.workload][0]
                                  if args.workload in NCU_TRAFFIC else None),
