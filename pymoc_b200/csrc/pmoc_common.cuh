@@ -33,8 +33,7 @@ static inline int fail(int code, const char* msg) {
 PM_DEV double vat(const pmoc_vec& v, long long m) { return v.ptr[m * v.mstride]; }
 PM_DEV const double* vrow(const pmoc_vec& v, long long m) { return v.ptr + m * v.mstride; }
 
-constexpr int kWarpsPerBlock = 4;      // per-module kernels
-constexpr int kMaxWarpsPerBlock = 16;  // fused kernel: chosen per launch (launch_model)
+constexpr int kWarpsPerBlock = 4;  // per-module kernels; the fused kernel picks its own per launch (launch_model)
 
 // ------------------------------------------------------------------------------------------
 // shared-memory plan (in doubles).  Per block: the grid tables; per warp (= member): the

@@ -45,9 +45,6 @@ def spec_from_cases(cases):
                             bzbot=None if d0['bzbot'] is None else g('bzbot'), N2min=g('N2min'),
                             do_conv=d0['do_conv'], var0=int(d0['var0']))
 
-  def fix_kappa(cs):  # ColumnSpec.build treats 2-D kappa as [M, nz]; golden kappa is [nvar, nz] per member
-    return cs
-
   basin, north = col('basin'), col('north')
   pac = col('pac') if c0.get('pac') is not None else None
   for cs, name in ((basin, 'basin'), (north, 'north'), (pac, 'pac')):

@@ -37,9 +37,6 @@ def run_against_golden(backend, name, nmax, tol=TOL, chunked=False):
   return worst
 
 
-def unit_column(backend, lib_call):
-  pass
-
 
 def diag_and_pickup_files(backend, tmpdir):
   """The --diagfile / --pickup_save_file archives of examples/run_JansenNadeau_2018.py:266-272 for
