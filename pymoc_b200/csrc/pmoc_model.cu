@@ -23,12 +23,15 @@ namespace pmk {
 #ifndef PM_WARPS_JN
 #define PM_WARPS_JN 12
 #endif
+#ifndef PM_WARPS_SINGLE
+#define PM_WARPS_SINGLE 16
+#endif
 #ifndef PM_PAC_BIT
 #define PM_PAC_BIT 0u  /* the three-column 'post' topology measured slower with this budget: 0.57 vs 0.62 */
 #endif
 constexpr int max_warps(unsigned topo) {
   return (topo & (PMOC_HAS_ML | PM_PAC_BIT)) ? PM_WARPS_JN
-                              : (((topo & PMOC_HAS_NORTH) && !(topo & PMOC_SO_BVP)) ? PM_WARPS_MULTI : 16);
+                              : (((topo & PMOC_HAS_NORTH) && !(topo & PMOC_SO_BVP)) ? PM_WARPS_MULTI : PM_WARPS_SINGLE);
 }
 
 template <int LPL, unsigned TOPO>
