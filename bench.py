@@ -43,6 +43,8 @@ WORKLOADS = {
     'C2': (lambda M: configs.c2_column_so(M), 65536, 7200),
     'twocol': (lambda M: configs.twocol(M), 32768, 2400),
     'C3': (lambda M: configs.c3_twocol_so(M), 32768, 2400),
+    # the literal script: F2010 smoother of Psi_GM (c = 0.1, bvp_with_Ek), parity at the stated 1e-5
+    'C3_bvp': (lambda M: configs.c3_twocol_so(M, c=0.1), 32768, 2400),
     'twobasin': (lambda M: configs.twobasin(M), 32768, 2400),
     'C4': (lambda M: configs.c4_jansen_nadeau(M), 32768, 2400),
     'C5': (lambda M: configs.c5_single_global_basin(M), 32768, 2400),
@@ -70,6 +72,8 @@ def algorithmic_flops(spec):
       refresh += nclos * (6 * B * (n - 1) + 8 * n + 2 * B + 2 * n * (math.ceil(math.log2(B)) + 5))
   if spec.so is not None:
     refresh += nclos * n * (math.ceil(math.log2(spec.so.y.size)) + 20)
+    if spec.so.c is not None:
+      refresh += 120 * n  # F2010 smoother (approximate)
   if spec.ml is not None:
     m = spec.ml.y.size
     per_step += m * (math.ceil(math.log2(n)) + 32) + n
