@@ -948,7 +948,7 @@ PM_DEV bool cell_propagators(const double (&Q0)[LPL], const double (&Q1)[LPL], d
     A[j] = 1.; Bh[j] = 1.; D[j] = 1.;
   }
   for (int k = 0; k < 600; ++k) {
-    const double inv = 1.0 / ((double)(k + 2) * (double)(k + 1)), kk = (double)(k + 2);
+    const double inv = rt::div_normal(1.0, (double)(k + 2) * (double)(k + 1)), kk = (double)(k + 2);
     bool big = false;
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
@@ -1014,7 +1014,7 @@ PM_DEV void so_bvp(double (&g)[LPL], const double (&b)[LPL], double c, double ya
   if (!cell_propagators<LPL>(Q0, Q1, A, Bh, D)) *status |= 32u;
   double ib[LPL];
   PM_UNROLL
-  for (int j = 0; j < LPL; ++j) ib[j] = 1.0 / (h[j] * Bh[j]);
+  for (int j = 0; j < LPL; ++j) ib[j] = rt::div_normal(1.0, h[j] * Bh[j]);  // h > 0, Bh >= 1
   const double ib_p = rt::shfl_up(ib[LPL - 1], 1), D_p = rt::shfl_up(D[LPL - 1], 1), Tp_p = rt::shfl_up(Tp[LPL - 1], 1);
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
@@ -1042,7 +1042,7 @@ PM_DEV void so_bvp(double (&g)[LPL], const double (&b)[LPL], double c, double ya
     const bool w = rt::lane() == 0;
     double cp = 0., dp = 0.;
     for (int i = 0; i < nz; ++i) {
-      const double l = lo_s[i], r = 1.0 / (di_s[i] - l * cp);
+      const double l = lo_s[i], r = rt::div_normal(1.0, di_s[i] - l * cp);  // diagonally dominant: pivots > 0
       cp = up_s[i] * r;
       dp = (rh_s[i] - l * dp) * r;
       if (w) { up_s[i] = cp; rh_s[i] = dp; }
