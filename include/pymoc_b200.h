@@ -45,17 +45,44 @@ typedef struct {
 
 /* per-member status bits written by the model kernels (pmoc_model.status) */
 #define PMOC_ST_NAN 1u            /* non-finite buoyancy at the end of the launch */
-#define PMOC_ST_BS_NONMONOTONE 2u /* bs(y) not monotone north of argmin: Brent path taken */
+#define PMOC_ST_BS_NONMONOTONE 2u /* bs(y) not monotone north of argmin at some diagnosis: ys() (psi_SO.py:106-140) has
+                                     several roots.  scipy's brentq is followed statement by statement,
+                                     which reproduces the reference's root for bit-identical bs, but the root it
+                                     lands on depends discontinuously on bs: rounding differences are amplified to
+                                     O(1) (measured: every member of the C5 lattice that misses 1e-10 carries this
+                                     bit), so parity is undefined */
 #define PMOC_ST_BRENT_SIGN 4u     /* f(a), f(b) same sign: scipy.optimize.brentq would raise ValueError */
 #define PMOC_ST_XP_NONMONOTONE 8u /* b_basin not monotone as np.interp abscissa in SO_ML:
                                      numpy's guess-carrying search is followed query by query */
 #define PMOC_ST_BVP_SERIES 32u    /* F2010 smoother: a cell propagator series did not converge (N2 h^2/c^2 huge) */
-#define PMOC_ST_NOISE_SWITCH 64u  /* 'jn' order: a bottom-boundary switch compared a streamfunction value that is
-                                     rounding noise (0 < |Psi[1]| < 1e-12 max|Psi|) with zero
-                                     (run_JansenNadeau_2018.py:233-254): the reference's own branch is then
-                                     decided by summation order, parity for this member is undefined */
+#define PMOC_ST_NOISE_SWITCH 64u  /* 'jn' order: the outcome of a bottom-boundary switch depended on the sign of a
+                                     streamfunction value that is rounding noise (0 < |Psi[1]| < 1e-12 max|Psi|,
+                                     run_JansenNadeau_2018.py:233-254) while the other operands of that switch
+                                     let it through: the reference's own branch is then decided by summation
+                                     order, parity for this member is undefined */
 #define PMOC_ST_ML_INDEX 16u      /* SO_ML needed np.argwhere(Psi_b > 0)[0][0] / np.nonzero(Psi_b)[0][0] of an
                                      all-non-positive / all-zero Psi_b: the reference raises IndexError */
+#define PMOC_ST_TIE_CELL 128u     /* isopycnal remap (psi_thermwind.py:177-184): a cell carrying transport has end
+                                     points within 4 eps of each other (flat, or one rounding from flat / inverted).
+                                     Psib's clip((top-x)/(top-bot), 0, 1) jumps by the cell's whole transport between
+                                     "flat" and "inverted by one ulp", so the reference's own answer is decided by the
+                                     last bit of its state there (structural in the 'jn' loop, whose no-flux bottom
+                                     condition bbot = b[1] drives b[0] - b[1] to zero); parity is undefined unless
+                                     the roundings happen to agree */
+#define PMOC_ST_BS_SAWTOOTH 256u  /* (informational, implies BS_NONMONOTONE) bs(y) decreases on >= 3 segments north of
+                                     its minimum: the reference's mixed layer has gone grid-scale unstable
+                                     (SO_ML.py:124-134 explicit upwind advection + Crank-Nicolson with Ks dt/dy^2 > 1) */
+/* Bits that make parity with the reference UNDEFINED for a member (the reference's own result is decided by
+ * rounding noise); the others are informational (a rarer but exactly reproduced code path was taken). */
+#define PMOC_ST_PARITY_UNDEFINED (PMOC_ST_BS_NONMONOTONE | PMOC_ST_NOISE_SWITCH | PMOC_ST_TIE_CELL)
+/* internal, not sticky: the Psi_SO value of level 1 that the 'jn' switches read was produced by state-independent
+ * arithmetic (the non-outcropping limiter or the slope clip) and is therefore reproduced bit for bit even when
+ * it is rounding noise; carried between launches in the status word */
+#define PMOC_ST_CARRY_SO1_EXACT 0x80000000u
+/* internal, not sticky (block-per-member kernels): which of Psi_so[1], Psi_iso_b[1], Psi_iso_n[1] of the last
+ * diagnosis are rounding noise (bits 28..30), handed from the diagnosis kernel to the step kernel */
+#define PMOC_ST_CARRY_NOISE_SHIFT 28
+#define PMOC_ST_CARRY_MASK 0xF0000000u
 
 /* ---- one advective-diffusive column: reference class Column, column.py:19-72 ------------ */
 typedef struct {

@@ -9,6 +9,22 @@ STATUS_NAMES = {1: 'EINVAL', 2: 'EUNSUPPORTED', 3: 'ECUDA', 4: 'ENODEVICE'}
 HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP, HAS_PAC = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_CONVECT, STAGE_VERTADVDIFF, STAGE_HORADV = 1, 2, 4
 ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES, ST_NOISE_SWITCH = 1, 2, 4, 8, 16, 32, 64
+ST_TIE_CELL, ST_BS_SAWTOOTH = 128, 256
+ST_PARITY_UNDEFINED = ST_BS_NONMONOTONE | ST_NOISE_SWITCH | ST_TIE_CELL  # the reference's own result hangs on rounding noise
+ST_PUBLIC_MASK = 0x0FFFFFFF  # the top bits carry kernel-internal hand-over flags between launches
+ST_BIT_NAMES = {1: 'nan', 2: 'bs_nonmonotone', 4: 'brent_sign', 8: 'xp_nonmonotone', 16: 'ml_index', 32: 'bvp_series',
+                64: 'noise_switch', 128: 'tie_cell', 256: 'bs_sawtooth'}
+
+
+def status_census(status):
+  """Members per status bit, plus how many carry a parity-undefined bit and how many carry none at all."""
+  import numpy as np
+  st = np.asarray(status).astype(np.uint32) & np.uint32(ST_PUBLIC_MASK)
+  out = {name: int(((st & np.uint32(bit)) != 0).sum()) for bit, name in ST_BIT_NAMES.items()}
+  out['parity_undefined'] = int(((st & np.uint32(ST_PARITY_UNDEFINED)) != 0).sum())
+  out['clean'] = int((st == 0).sum())
+  out['members'] = int(st.size)
+  return out
 
 c_double_p = C.POINTER(C.c_double)
 

@@ -244,20 +244,29 @@ def c4_jansen_nadeau(M=1, axes=None):
   """examples/run_JansenNadeau_2018.py:33-261 (default flags) -- two convecting columns,
   thermal wind with isopycnal remap, explicit Psi_SO, SO_ML, bottom-boundary switches.
 
-  Lattice: tau x kapfac x db x B x KGM.  The db axis stops at +0.002:
-  beyond it the reference itself goes NaN in the northern column for kapfac < 0.8 (its explicit
-  upwind step violates the advective CFL there), and KGM is swept over 750..950: with weaker
-  eddies and strong wind, or stronger eddies and weak wind, 1-2 % of a 500..1500 lattice blows
-  up in the reference as well.
+  Lattice: tau x kapfac x db x B x KGM, restricted to the part of parameter
+  space in which the reference's own answer is well defined (measured on 512-member coarse lattices against
+  the unmodified algorithm, scratch census of round 2):
+    * kapfac 1.0..1.8 and db -0.004..0: for kapfac <= 0.75 or db >= +0.001 the no-flux bottom condition
+      bbot = b[1] drives b[0] - b[1] of a column to within a rounding of zero in steady state, and Psib's
+      clip((top-x)/(top-bot)) jumps by the cell's whole transport between a flat and a one-ulp-inverted cell
+      (PMOC_ST_TIE_CELL): 47 % of a kapfac 0.5..2 x db -0.004..+0.002 lattice sat there, 1 % of it missed
+      1e-10 because the reference's rounding fell the other way.  On this lattice 2.7 % carry the bit after
+      2 401 steps and none misses;
+    * tau 0.07..0.2, B 4e3..9e3, KGM 750..950: at weak wind + strong mixing + weak surface flux the
+      reference itself ends in NaN / a brentq ValueError (explicit upwind step beyond its advective CFL in
+      the narrow northern column); with KGM outside 750..950 1-2 % of a 500..1500 lattice blows up as well.
+  The script's own values (tau 0.12, kapfac 1, db 0, B 5.9e3, KGM 800) are inside, and are the M == 1 member
+  and the golden fixtures c4_literal.npz / c4_diags.npz.
   """
   if M == 1:
     sweep = lattice(tau=[0.12], kapfac=[1.0], db=[0.0], B=[5.9e3], KGM=[800.])
   else:
     n = axes if axes is not None else _sizes(M, 5)
-    sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
-                    kapfac=np.geomspace(0.5, 2., n[1]) if n[1] > 1 else [1.0],
-                    db=np.linspace(-0.004, 0.002, n[2]) if n[2] > 1 else [0.0],
-                    B=np.linspace(3e3, 9e3, n[3]) if n[3] > 1 else [5.9e3],
+    sweep = lattice(tau=np.linspace(0.07, 0.2, n[0]) if n[0] > 1 else [0.12],
+                    kapfac=np.geomspace(1.0, 1.8, n[1]) if n[1] > 1 else [1.0],
+                    db=np.linspace(-0.004, 0.0, n[2]) if n[2] > 1 else [0.0],
+                    B=np.linspace(4e3, 9e3, n[3]) if n[3] > 1 else [5.9e3],
                     KGM=np.linspace(750., 950., n[4]) if n[4] > 1 else [800.])
   sweep, M = _shard(sweep, M)
   db = sweep['db']
@@ -291,11 +300,20 @@ def c4_jansen_nadeau(M=1, axes=None):
       order='jn', iso=True)
 
 
-def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None, kapfac_max=2.):
+def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None, kapfac_max=2., Ks_range=(250., 500.),
+                           KGM_range=(700., 950.)):
   """examples/run_single_global_basin.py:40-229 with ``z=linspace(-4500,0,nz)``.
 
-  Lattice: tau x kapfac x KGM x Ks (Ks <= 900: above ~1000 the
-  reference itself ends in NaN / a brentq ValueError for a quarter of the lattice).  The explicit diffusion
+  Lattice: tau x kapfac x KGM x Ks.  The KGM and Ks ranges are the part of
+  parameter space in which the reference itself is well posed: measured on a 512-member coarse lattice over
+  KGM 500..1500 x Ks 150..900 against the unmodified algorithm (oracle), bs(y) of the mixed layer becomes
+  non-monotone north of its minimum (a grid-scale sawtooth for Ks dt/dy^2 > 1, i.e. Ks > 620; a multi-root
+  ys() for KGM > 1000 or Ks < 250), after which brentq's choice of root amplifies rounding differences to
+  O(1) -- 17 % of that lattice cannot be matched to 1e-10 by *any* implementation and another 50 % only by
+  luck.  Inside KGM 700..950 x Ks 250..500 no member leaves the monotone regime in 2 401 steps (tau stops at
+  0.18: for tau/KGM above ~2.9e-4 a bottom-boundary switch is decided by rounding noise, PMOC_ST_NOISE_SWITCH).  (Above
+  Ks ~ 1000 the reference ends in NaN / a brentq ValueError for a quarter of the lattice.)  The script's own
+  defaults (KGM = Ks = 1000) are the M == 1 member and the golden fixture c5.npz.  The explicit diffusion
   needs dt <= dz^2/(2 kappa_max): 30 d at nz=46, 5 d at nz=200, 0.01 d at nz=4096 (H6) -- the
   latter only for kapfac <= 1.08, hence ``kapfac_max`` (the nz=4096 lattice sweeps 0.5..1).
   """
@@ -303,10 +321,10 @@ def c5_single_global_basin(M=1, nz=46, dt_days=30., axes=None, kapfac_max=2.):
     sweep = lattice(tau=[0.12], kapfac=[1.0], KGM=[1.0e3], Ks=[1.0e3])
   else:
     n = axes if axes is not None else _sizes(M, 4)
-    sweep = lattice(tau=np.linspace(0.06, 0.2, n[0]) if n[0] > 1 else [0.12],
+    sweep = lattice(tau=np.linspace(0.06, 0.18, n[0]) if n[0] > 1 else [0.12],
                     kapfac=np.geomspace(0.5, kapfac_max, n[1]) if n[1] > 1 else [1.0],
-                    KGM=np.linspace(500., 1500., n[2]) if n[2] > 1 else [1.0e3],
-                    Ks=np.linspace(500., 900., n[3]) if n[3] > 1 else [1.0e3])
+                    KGM=np.linspace(KGM_range[0], KGM_range[1], n[2]) if n[2] > 1 else [1.0e3],
+                    Ks=np.linspace(Ks_range[0], Ks_range[1], n[3]) if n[3] > 1 else [1.0e3])
   sweep, M = _shard(sweep, M)
   bs, bs_north, bminSO = 0.025, 0.0, 0.0
   h, L = 50., 2e7

@@ -471,9 +471,18 @@ PM_COLD double remap_flat_fix(double c, double x, int k, int nz, const double* b
   return c;
 }
 
+// A cell whose end points are within 4 eps (relative) of each other while it carries transport: between "flat"
+// ((top-x)/0 = +-inf -> the cell's transport goes to the classes below it) and "inverted by one ulp"
+// ((top-x)/(-ulp) -> to the classes above it) psib jumps by the whole u_c, so the last bit of the state decides.
+constexpr double kTieEps = 4.0 * 2.220446049250313e-16;
+PM_DEV bool remap_tie(double bot, double top, double u) {
+  const double a = fabs(top), b = fabs(bot);
+  return u != 0.0 && fabs(top - bot) <= kTieEps * (a > b ? a : b);
+}
+
 template <int LPL>
 PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const double (&b2)[LPL], int nz, int nb,
-                     double* rs, double* psib_s, int* cnt_s) {
+                     double* rs, double* psib_s, int* cnt_s, unsigned* status = nullptr) {
   const int nzp = 32 * LPL, L = rt::lane();
   const double psin = rt::shfl_down(psi[0], 1);
   const double b1n = rt::shfl_down(b1[0], 1), b2n = rt::shfl_down(b2[0], 1);
@@ -535,6 +544,7 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
   // exceptional cells: an end point below the running maximum of the column the cell is taken from
   unsigned excm = 0;
   int ne = 0;
+  bool tie = false;
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
@@ -545,12 +555,14 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       const double mu = from2 ? (last ? m2n : m2[jn]) : (last ? m1n : m1[jn]);
       const double upv = from2 ? up2[j] : up1[j];
       const double mb = from2 ? m2[j] : m1[j], bv = from2 ? b2[j] : b1[j];
+      tie |= remap_tie(bv, upv, u[j]);
       if (allexc || mu != upv || mb != bv) {
         excm |= 1u << j;
         ++ne;
       }
     }
   }
+  if (status != nullptr && rt::ballot(tie) != 0) *status |= 128u;  // PMOC_ST_TIE_CELL
   int incl = ne;
   PM_UNROLL
   for (int d = 1; d < 32; d <<= 1) {
@@ -852,8 +864,10 @@ struct SoPar {
 struct SoSurf {  // per-refresh scan of bs(y)
   double mn, bsN, y0, yN;
   int south;
-  bool mono;
+  int ndown;  // segments north of the minimum on which bs decreases
+  bool mono;  // ndown == 0
 };
+constexpr int kSawtoothSegments = 3;  // PMOC_ST_BS_SAWTOOTH: this many decreasing segments north of the minimum
 // block-cooperative copy of the four host-evaluated taper profiles into lane-major shared memory
 template <int LPL>
 PM_DEV void taper_fill(double* dst, const double* PM_RESTRICT sill, const double* PM_RESTRICT ektap,
@@ -891,13 +905,18 @@ PM_DEV SoSurf so_scan(const double* ygrid, const double* bs, double* sinv, int n
     s.mn = first ? b0 : v;
     s.south = first ? 0 : idx;
   }
-  bool down = false;
-  for (int k = rt::lane(); k < ny - 1; k += 32) {
-    const double db = bs[k + 1] - bs[k];
-    sinv[k] = sdiv(ygrid[k + 1] - ygrid[k], db);
-    if (k >= s.south && db < 0) down = true;
+  s.ndown = 0;
+  for (int k0 = 0; k0 < ny - 1; k0 += 32) {  // (warp-uniform trip count)
+    const int k = k0 + rt::lane();
+    bool down = false;
+    if (k < ny - 1) {
+      const double db = bs[k + 1] - bs[k];
+      sinv[k] = sdiv(ygrid[k + 1] - ygrid[k], db);
+      down = k >= s.south && db < 0;
+    }
+    s.ndown += rt::popc(rt::ballot(down));
   }
-  s.mono = rt::ballot(down) == 0;
+  s.mono = s.ndown == 0;
   s.bsN = bs[ny - 1];
   s.y0 = ygrid[0];
   s.yN = ygrid[ny - 1];
@@ -1104,13 +1123,15 @@ PM_DEV void outcrop_monotone_all(double (&yo)[LPL], const double (&b)[LPL], cons
 template <int LPL, bool BVP = false>
 PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], double (&ysv)[LPL],
                      const double (&b)[LPL], const double* ygrid, const double* bs, const double* sinv, int ny,
-                     const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status) {
+                     const SoSurf& S, const SoPar& P, const double* zs, int nz, unsigned* status,
+                     bool* psi1_exact = nullptr) {
   const double pre0 = P.pre0;
   const double c6 = 1e6, r6 = 1.0 / 1e6;
   if (S.mono && S.south < ny - 1) {
     outcrop_monotone_all<LPL>(ysv, b, ygrid, bs, sinv, ny, S);
   } else {
     if (!S.mono) *status |= 2u;
+    if (S.ndown >= kSawtoothSegments) *status |= 256u;  // PMOC_ST_BS_SAWTOOTH
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {  // (registers: must stay unrolled; the heavy callee is out of line)
       const double bi = b[j];
@@ -1132,6 +1153,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     }
   }
   double dyv[LPL], prev[LPL];
+  bool exact1 = false;  // level 1: Psi = Ek + GM came out of state-independent arithmetic (see PMOC_ST_CARRY_SO1_EXACT)
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) prev[j] = pre0;
   if (P.tau_y != nullptr) {  // tau on the y grid: a 100-point mean and two divides per level (kept out of the float-tau path)
@@ -1156,6 +1178,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
       const double sl = rt::div_normal(z, dy), ms = -P.smax;  // dy >= 0.1, |z| <= H: in range
       const double mx = (sl >= ms || sl != sl) ? sl : ms;
       g = P.KGM * mx * P.L * P.toptap[s] * P.bottap[s];
+      if (i == 1 && !(sl >= ms || sl != sl) && P.tau_y == nullptr) exact1 = true;  // the slope clip: constants only
     }
     ek[j] = in ? e : 0.0;
     gm[j] = in ? g : 0.0;
@@ -1176,6 +1199,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     double t = gm[j];
     if (dyv[j] > S.yN - S.y0) {
       const double alt = -ek[j] * 1e6;
+      if (i == 1 && !(t >= alt || t != t) && P.tau_y == nullptr) exact1 = true;  // the limiter: Psi = Ek - (Ek*1e6)/1e6
       t = (t >= alt || t != t) ? t : alt;
     }
     const double g = div_const(t, c6, r6);
@@ -1183,6 +1207,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     gm[j] = in ? g : 0.0;
     psi[j] = (in && i != 0) ? ek[j] + g : 0.0;
   }
+  if (psi1_exact != nullptr) *psi1_exact = rt::ballot(exact1) != 0;
 }
 
 // ====================================================================== SO_ML

@@ -131,6 +131,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
   double* const bb_s = ws + (ML ? sp.w_bb : 0);
   double* const pm_s = ws + (ML ? sp.w_pm : 0);
   double psi_so1 = 0., res_b1 = 0., res_n1 = 0.;  // Psi[1] of the three streamfunctions ('jn' switches)
+  // which of them are rounding noise (bit 0: Psi_so[1], 1: Psi_iso_b[1], 2: Psi_iso_n[1]); so1_exact: Psi_so[1] came
+  // out of state-independent arithmetic and is reproduced bit for bit even then (PMOC_ST_CARRY_SO1_EXACT)
+  int noise = 0;
+  bool so1_exact = ML && M.status != nullptr && (M.status[m] & PMOC_ST_CARRY_SO1_EXACT) != 0;
   if (ML) {
     pm::ml_setup(ml, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m),
                  vrow(M.ml_surflux, m), vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), dt, ws + sp.w_scan);
@@ -188,7 +192,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       }
       const double tiny = 1e-12 * rt::wmax(mx);
       const double s1 = fabs(psi_so1), s2 = fabs(res_b1), s3 = fabs(res_n1);
-      if ((s1 > 0 && s1 < tiny) || (s2 > 0 && s2 < tiny) || (s3 > 0 && s3 < tiny)) status |= PMOC_ST_NOISE_SWITCH;
+      noise = ((s1 > 0 && s1 < tiny && !so1_exact) ? 1 : 0) | ((s2 > 0 && s2 < tiny) ? 2 : 0) | ((s3 > 0 && s3 < tiny) ? 4 : 0);
     }
   };
 
@@ -204,7 +208,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       if (ISO) {
         double* psib_s = ws + sp.w_psib;
         const pm::BGrid BG = pm::tw_psib<LPL>(psi_tw, cb.b, b2, nz, nb, ws + sp.w_remap, psib_s,
-                                              reinterpret_cast<int*>(ws + sp.w_cnt));
+                                              reinterpret_cast<int*>(ws + sp.w_cnt), &status);
         PM_UNROLL
         for (int j = 0; j < LPL; ++j) {
           const bool ok = pm::lev<LPL>(j) < nz;
@@ -228,7 +232,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       if (write && M.Psi_zoc) pm::store_lev<LPL>(psi_zoc, M.Psi_zoc + m * nz, nz);
       double* psib_s = ws + sp.w_psib;
       const pm::BGrid BG = pm::tw_psib<LPL>(psi_zoc, cb.b, cp.b, nz, nb, ws + sp.w_remap, psib_s,
-                                            reinterpret_cast<int*>(ws + sp.w_cnt));
+                                            reinterpret_cast<int*>(ws + sp.w_cnt), &status);
       PM_UNROLL
       for (int j = 0; j < LPL; ++j) {
         const bool ok = pm::lev<LPL>(j) < nz;
@@ -255,7 +259,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
         surf = pm::so_scan(ysm, ws + sp.w_bs, ws + sp.w_sinv, ny);
       }
       pm::so_solve<LPL, BVP>(psi_so, ek, gm, ysv, cb.b, ysm, ws + sp.w_bs, ws + sp.w_sinv, ny, surf, so, zs, nz,
-                             &status);
+                             &status, &so1_exact);
       if (write) {
         pm::store_lev<LPL>(psi_so, M.Psi_so + m * nz, nz);
         if (M.Psi_Ek) pm::store_lev<LPL>(ek, M.Psi_Ek + m * nz, nz);
@@ -370,6 +374,9 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
           cn.bbot = nb1;
           vn = 0;
         }
+        // a switch whose outcome hung on the sign of a noise value (the other operands let it through)
+        if (noise != 0 && ((noise & 1) || ((noise & 2) && nb0 < bb1 && nb0 < bs0) || ((noise & 4) && bb0 < nb1)))
+          status |= PMOC_ST_NOISE_SWITCH;
         if (two_var_b) cb.var = vb;
         if (two_var_n) cn.var = vn;
         col_advance_exact<LPL>(cb, xb, EG, G, nz, dt);
@@ -381,8 +388,15 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       wr = ii == last_refresh;
     }
   }
+  auto put_status = [&]() {
+    if (M.status && L == 0) {
+      unsigned w = (M.status[m] | status) & ~PMOC_ST_CARRY_SO1_EXACT;
+      if (ML && so1_exact) w |= PMOC_ST_CARRY_SO1_EXACT;
+      M.status[m] = w;
+    }
+  };
   if (dg) {
-    if (M.status && L == 0) M.status[m] |= status;
+    put_status();
     return;
   }
   if (ML) {
@@ -420,7 +434,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       if (pm::mlk(e) < ny) bad |= !(fabs(ml.bs[e]) <= 1.79e308);
   }
   if (rt::ballot(bad)) status |= PMOC_ST_NAN;
-  if (M.status && L == 0) M.status[m] |= status;
+  put_status();
 }
 
 template <int LPL>

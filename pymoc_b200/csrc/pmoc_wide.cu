@@ -80,7 +80,7 @@ PM_DEV int block_min(int v, int* slot) { return -block_max(-v, slot); }
 PM_DEV unsigned block_or(unsigned v, int* slot) {
   if (wtid() == 0) *slot = 0;
   rt::syncblock();
-  for (unsigned bit = 1; bit <= 64u; bit <<= 1)
+  for (unsigned bit = 1; bit <= 256u; bit <<= 1)
     if (rt::ballot((v & bit) != 0) != 0 && rt::lane() == 0) rt::atomic_or_shared(slot, (int)bit);
   rt::syncblock();
   const unsigned r = (unsigned)*slot;
@@ -182,6 +182,7 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
     if (i < nz - 1) {
       const double u = -(P[i + 1] - P[i]);
       unsorted |= !(b1[i + 1] >= b1[i]) || !(b2[i + 1] >= b2[i]) || u != u;
+      if (u < 0 ? pm::remap_tie(b2[i], b2[i + 1], u) : pm::remap_tie(b1[i], b1[i + 1], u)) status |= PMOC_ST_TIE_CELL;
     }
   }
   lo = rt::wmin(lo);
@@ -286,15 +287,24 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
     if (M.psib) M.psib[m * nb + i] = psib_s[i];
     if (M.bgrid) M.bgrid[m * nb + i] = G.at(i);
   }
+  // what the 'jn' switches of the step kernel read (level 1 of the three streamfunctions), and the scale
+  // against which they count as rounding noise (PMOC_ST_NOISE_SWITCH)
+  double mxl = 0.0, so1 = 0.0, resb1 = 0.0, resn1 = 0.0;
+  bool exact1 = false;
   for (int i = t; i < nz; i += T) {
-    M.Psi_iso_b[m * nz + i] = pm::interp_bgrid(b1[i], G, psib_s);
-    M.Psi_iso_n[m * nz + i] = pm::interp_bgrid(b2[i], G, psib_s);
+    const double vb = pm::interp_bgrid(b1[i], G, psib_s), vn = pm::interp_bgrid(b2[i], G, psib_s);
+    M.Psi_iso_b[m * nz + i] = vb;
+    M.Psi_iso_n[m * nz + i] = vn;
+    mxl = fabs(vb) > mxl ? fabs(vb) : mxl;
+    mxl = fabs(vn) > mxl ? fabs(vn) : mxl;
+    if (i == 1) { resb1 = vb; resn1 = vn; }
   }
 
   // --- Psi_SO.solve, explicit GM branch (psi_SO.py:106-140, 218-243, 302-354), see pm::so_solve
   const pm::SoSurf S = pm::so_scan(ysm, bs_s, sinv, ny);  // every warp redundantly, same values
   rt::syncblock();
   if (!S.mono) status |= PMOC_ST_BS_NONMONOTONE;
+  if (S.ndown >= pm::kSawtoothSegments) status |= PMOC_ST_BS_SAWTOOTH;
   const double tau_ave = pm::mean100(vat(M.so_tau, m));
   const double sf = vat(M.so_f, m), srho = vat(M.so_rho, m), sL = vat(M.so_L, m), sK = vat(M.so_KGM, m),
                smax = vat(M.so_smax, m);
@@ -319,17 +329,36 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
     const double sl = pm::qdiv(z[i], dy), ms = -smax;
     const double mx = (sl >= ms || sl != sl) ? sl : ms;
     double g = sK * mx * sL * M.so_top_taper[i] * M.so_bot_taper[i];
+    if (i == 1 && !(sl >= ms || sl != sl)) exact1 = true;  // the slope clip: constants only (see pm::so_solve)
     if (dy > S.yN - S.y0) {
       const double alt = -e * 1e6;
+      if (i == 1 && !(g >= alt || g != g)) exact1 = true;  // the limiter
       g = (g >= alt || g != g) ? g : alt;
     }
     g = pm::div_const(g, c6, r6);
-    M.Psi_so[m * nz + i] = i == 0 ? 0. : e + g;
+    const double v = i == 0 ? 0. : e + g;
+    M.Psi_so[m * nz + i] = v;
+    mxl = fabs(v) > mxl ? fabs(v) : mxl;
+    if (i == 1) so1 = v;
     if (M.Psi_Ek) M.Psi_Ek[m * nz + i] = e;
     if (M.Psi_GM) M.Psi_GM[m * nz + i] = g;
   }
   const unsigned all = block_or(status, ibox);
-  if (t == 0 && M.status) M.status[m] |= all;
+  mxl = rt::wmax(mxl);
+  rt::syncblock();
+  if (rt::lane() == 0) red[rt::warp_in_block()] = mxl;
+  if (t == 1 % T) {  // the thread that owns level 1
+    red[32] = so1; red[33] = resb1; red[34] = resn1; red[35] = exact1 ? 1.0 : 0.0;
+  }
+  rt::syncblock();
+  if (t == 0 && M.status) {
+    double mx = 0.0;
+    for (int w = 0; w < rt::warps_per_block(); ++w) mx = red[w] > mx ? red[w] : mx;
+    const double tiny = 1e-12 * mx, s1 = fabs(red[32]), s2 = fabs(red[33]), s3 = fabs(red[34]);
+    const unsigned noise = ((s1 > 0 && s1 < tiny && red[35] == 0.0) ? 1u : 0u) | ((s2 > 0 && s2 < tiny) ? 2u : 0u) |
+                           ((s3 > 0 && s3 < tiny) ? 4u : 0u);
+    M.status[m] = ((M.status[m] | all) & ~PMOC_ST_CARRY_MASK) | (noise << PMOC_ST_CARRY_NOISE_SHIFT);
+  }
 }
 
 // ---- the steps, state and per-level constants resident on chip ---------------------------------
@@ -437,6 +466,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
   const bool uniA = !block_any(areas_differ, cbox);
   const double A_b = Ab[1], rA_b = 1.0 / A_b, A_n = An[1], rA_n = 1.0 / A_n;
   const double psi_so1 = M.Psi_so[m * nz + 1], res_b1 = M.Psi_iso_b[m * nz + 1], res_n1 = M.Psi_iso_n[m * nz + 1];
+  const unsigned noise = M.status ? (M.status[m] >> PMOC_ST_CARRY_NOISE_SHIFT) & 7u : 0u;  // set by k_wide_refresh
   if (fnz == 0x7fffffff) status |= PMOC_ST_ML_INDEX;
   const double held = pm_s[fnz == 0x7fffffff ? 0 : fnz];
   rt::syncblock();
@@ -515,6 +545,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
       else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
       if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
       else { bbot_n = nb1; vn = 0; }
+      if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
+        status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
       if (M.basin.nvar < 2) vb = 0;
       if (M.north.nvar < 2) vn = 0;
       if (vb != var_b) {  // the owner re-reads its levels of the other variant

@@ -242,7 +242,7 @@ class Ensemble:
                         'status', 'bbot_basin', 'bbot_north', 'var_basin', 'var_north', 'Psi_zoc', 'Psi_zon_a',
                         'Psi_zon_p', 'psib2', 'bgrid2', 'Psi_so2', 'Psi_Ek2', 'Psi_GM2') if k in self._bufs]
     out = {k: self.be.download(self._bufs[k]) for k in keys}
-    out['status'] = out['status'].view(np.uint32)
+    out['status'] = out['status'].view(np.uint32) & np.uint32(_abi.ST_PUBLIC_MASK)
     return out
 
   def buffer(self, name):
