@@ -74,7 +74,7 @@ def c1_timestepping(M=1, nz=70):
   if M == 1:
     kappa, sweep = kap(z), {}
   else:  # scale the diffusivity profile (dt = 60 d is diffusively stable up to kapfac ~ 1.37)
-    sweep = lattice(kapfac=np.linspace(0.5, 1.25, M))
+    sweep, M = _shard(lattice(kapfac=np.linspace(0.5, 1.25, M)), M)
     kappa = sweep['kapfac'][:, None] * kap(z)[None, :]
   return ModelSpec(
       M=M, z=z, dt=60 * DAY, K=1, name='C1 example_timestepping', sweep=sweep,
@@ -116,8 +116,10 @@ def twocol(M=1):
   dt = 86400 * 30
   K = int(np.floor(2 * 360 * 86400 / dt))
   kap = 1e-5 + 3e-4 * np.exp(-z / 1000 - 4)
+  lattice_M = M
   sweep = lattice(kapfac=np.linspace(0.5, 1.25, M)) if M > 1 else {}  # above ~1.3 the explicit step is unstable
-  kappa = kap if M == 1 else sweep['kapfac'][:, None] * kap[None, :]
+  sweep, M = _shard(sweep, M)
+  kappa = kap if lattice_M == 1 else sweep['kapfac'][:, None] * kap[None, :]
   return ModelSpec(
       M=M, z=z, dt=dt, K=K, name='example_twocol', sweep=sweep,
       basin=ColumnSpec.build(z, kappa, A, bs, bs * np.exp(z / 300.), bbot=bbot),
@@ -240,7 +242,16 @@ def _channel_surface(y, l, bs, bminSO, Bloss):
   return eq, surflux, rest_mask
 
 
-def c4_jansen_nadeau(M=1, axes=None):
+def _explicit(sweep, names):
+  """A caller-supplied sweep (dict of equally long per-member arrays) instead of a lattice."""
+  out = {k: np.ascontiguousarray(np.atleast_1d(np.asarray(sweep[k], dtype=np.float64))) for k in names}
+  sizes = {v.size for v in out.values()}
+  if len(sizes) != 1:
+    raise ValueError('sweep arrays must have equal lengths, got %r' % {k: v.size for k, v in out.items()})
+  return out, sizes.pop()
+
+
+def c4_jansen_nadeau(M=1, axes=None, sweep=None):
   """examples/run_JansenNadeau_2018.py:33-261 (default flags) -- two convecting columns,
   thermal wind with isopycnal remap, explicit Psi_SO, SO_ML, bottom-boundary switches.
 
@@ -259,7 +270,9 @@ def c4_jansen_nadeau(M=1, axes=None):
   The script's own values (tau 0.12, kapfac 1, db 0, B 5.9e3, KGM 800) are inside, and are the M == 1 member
   and the golden fixtures c4_literal.npz / c4_diags.npz.
   """
-  if M == 1:
+  if sweep is not None:  # explicit parameter sets: {tau, kapfac, db, B, KGM} -> one member each
+    sweep, M = _explicit(sweep, ('tau', 'kapfac', 'db', 'B', 'KGM'))
+  elif M == 1:
     sweep = lattice(tau=[0.12], kapfac=[1.0], db=[0.0], B=[5.9e3], KGM=[800.])
   else:
     n = axes if axes is not None else _sizes(M, 5)

@@ -94,6 +94,10 @@ class ChannelSpec:
 
   ``tau`` is one float per member (every example does this) or an array on ``y`` per
   member.  The four taper heights are shared by the ensemble.
+
+  Shapes: a 0-D / 1-D ``tau`` is read as one float per member (length 1 or M); a wind stress profile on the
+  y grid must be 2-D, ``[1, ny]`` (shared) or ``[M, ny]`` -- the reference accepts a bare ``[ny]`` array for
+  its single model, here that would be ambiguous with M == ny members and is rejected by ``ModelSpec``.
   """
   y: np.ndarray  # [ny]
   bs: np.ndarray  # [1|M, ny]
@@ -201,6 +205,51 @@ class ModelSpec:
       if self.zoc_f is None or self.so_pac_L is None:
         raise ValueError('pac needs zoc_f and so_pac_L')
       self.zoc_f, self.so_pac_L = _vec(self.zoc_f, 'zoc_f'), _vec(self.so_pac_L, 'so_pac_L')
+
+    self._check_member_axes()
+
+  def _check_member_axes(self):
+    """Every per-member array must have a leading dimension of 1 (shared by all members) or M.  A short array
+    would otherwise be uploaded as it is and read out of bounds on the device for members beyond its length
+    (e.g. a wind stress given on the ny-point y grid as a 1-D array: that must be passed as [1, ny])."""
+    nz, M = self.z.size, int(self.M)
+
+    def chk(owner, name, a, trailing):
+      if a is None:
+        return
+      a = np.asarray(a)
+      if a.ndim != 1 + len(trailing) or tuple(a.shape[1:]) != tuple(trailing) or a.shape[0] not in (1, M):
+        raise ValueError('%s.%s: shape %r, expected (1|%d%s)' % (owner, name, a.shape, M, ''.join(', %d' % t for t in trailing)))
+
+    for tag, c in (('basin', self.basin), ('north', self.north), ('pac', self.pac)):
+      if c is None:
+        continue
+      if c.kappa.ndim != 3 or c.kappa.shape[2] != nz or c.kappa.shape[0] not in (1, M) or c.kappa.shape[1] not in (1, 2):
+        raise ValueError('%s.kappa: shape %r, expected (1|%d, 1|2 variants, %d); a [nvar, nz] array must be given as '
+                         '[1, nvar, nz]' % (tag, c.kappa.shape, M, nz))
+      if not 0 <= c.var0 < c.kappa.shape[1]:
+        raise ValueError('%s.var0 = %d outside the %d kappa variant(s)' % (tag, c.var0, c.kappa.shape[1]))
+      for name, tr in (('Area', (nz,)), ('b0', (nz,)), ('bs', ()), ('bbot', ()), ('N2min', ()), ('bzbot', ())):
+        chk(tag, name, getattr(c, name), tr)
+    if self.tw is not None:
+      chk('tw', 'f', self.tw.f, ())
+      chk('tw', 'b2', self.tw.b2, (nz,))
+    if self.so is not None:
+      so, ny = self.so, self.so.y.size
+      chk('so', 'bs', so.bs, (ny,))
+      chk('so', 'tau', so.tau, (ny,) if so.tau.ndim == 2 else ())
+      for name in ('f', 'rho', 'L', 'KGM', 'smax', 'c'):
+        chk('so', name, getattr(so, name), ())
+    if self.ml is not None:
+      ml, ny = self.ml, self.ml.y.size
+      if self.so is not None and ny != self.so.y.size:
+        raise ValueError('ml.y and so.y must be the same grid')
+      for name in ('Ks', 'h', 'L', 'v_pist'):
+        chk('ml', name, getattr(ml, name), ())
+      for name in ('surflux', 'rest_mask', 'b_rest', 'bs0'):
+        chk('ml', name, getattr(ml, name), (ny,))
+    chk('model', 'zoc_f', self.zoc_f, ())
+    chk('model', 'so_pac_L', self.so_pac_L, ())
 
   @property
   def nz(self):

@@ -108,3 +108,93 @@ def edge_sizes(backend, wide=True):
       spec = configs.c5_single_global_basin(1, nz=nz, dt_days=dt_days)
       check(spec, 25, (0,), ('b_basin', 'b_north', 'bs_ml', 'Psi_iso_b', 'Psi_so'))
   return worst
+
+
+# ------------------------------------------------------------------------------------------------
+# Bench-lattice samples against the live oracle: the golden fixtures hold a handful
+# of members; the bench steps 32k..262k-member lattices.  These checks draw seeded-random members from the
+# BENCH-SIZE lattice (the very members bench.py runs), step them through the kernel as one ensemble and compare
+# every one of them with the oracle.  Contract:
+#   * a member that carries none of the PMOC_ST_PARITY_UNDEFINED bits must match to `tol` in every field;
+#   * a member the oracle loses (NaN state, or the ValueError / IndexError the reference raises) must be
+#     flagged by the kernel (PMOC_ST_NAN / BRENT_SIGN / ML_INDEX), and vice versa;
+#   * the fraction of members carrying a parity-undefined bit stays below `max_flagged`, and how many of those
+#     nevertheless match is reported.
+LATTICE_FIELDS = ('b_basin', 'b_north', 'b_pac', 'bs_ml', 'Psi_tw', 'Psi_iso_b', 'Psi_iso_n', 'Psi_so', 'Psi_zon_a',
+                  'Psi_zon_p', 'Psi_so2')
+
+
+def bench_lattice(workload, M):
+  """The bench's own builder for `workload` at lattice size M (imports bench.py: same lattice, by construction)."""
+  import bench
+  return bench.WORKLOADS[workload][0](M)
+
+
+def sample_cases(workload, M, nsample, seed):
+  """`nsample` seeded-random members of the M-member bench lattice of `workload`, as oracle cases."""
+  from pymoc_b200 import configs
+  rng = np.random.default_rng(seed)
+  ms = sorted(int(m) for m in rng.choice(M, size=min(nsample, M), replace=False))
+  cases = []
+  for m in ms:
+    with configs.members(m, m + 1):  # only this member of the lattice is materialised
+      cases.append(bench_lattice(workload, M).member_case(0))
+  return ms, cases
+
+
+def _oracle_task(args):
+  case, nsteps = args
+  import warnings
+  warnings.filterwarnings('ignore')
+  from oracle import pymoc_oracle as O
+  try:
+    out = O.run_coupled(case, nsteps, O.REFERENCE)
+    return {k: v for k, v in out.items() if v is not None}
+  except (ValueError, IndexError, FloatingPointError) as e:  # what the reference raises on a lost member
+    return repr(e)
+
+
+def oracle_many(cases, nsteps, procs=None):
+  """The oracle's reference-faithful loop for every case, on the host cores (spawned workers: safe next to CUDA)."""
+  import multiprocessing as mp
+  import os
+  procs = procs or min(len(cases), os.cpu_count() or 1)
+  if procs <= 1:
+    return [_oracle_task((c, nsteps)) for c in cases]
+  with mp.get_context('spawn').Pool(procs) as pool:
+    return pool.map(_oracle_task, [(c, nsteps) for c in cases], chunksize=1)
+
+
+def lattice_sample(backend, workload, M, nsample, nsteps, seed=0, tol=TOL, max_flagged=1.0, procs=None):
+  from pymoc_b200 import _abi
+  ms, cases = sample_cases(workload, M, nsample, seed)
+  ens = Ensemble(spec_from_cases(cases), backend=backend)
+  ens.run(nsteps)
+  got = {**ens.state(), **ens.diagnostics()}
+  want = oracle_many(cases, nsteps, procs)
+  st = got['status']
+  rep = dict(workload=workload, lattice=M, sampled=len(ms), steps=nsteps, census=_abi.status_census(st), worst_unflagged=0.0,
+             flagged_matching=0, flagged_missing=0, lost_by_both=0)
+  for i, m in enumerate(ms):
+    undefined = bool(st[i] & _abi.ST_PARITY_UNDEFINED)
+    lost_k = bool(st[i] & (_abi.ST_NAN | _abi.ST_BRENT_SIGN | _abi.ST_ML_INDEX))
+    w = want[i]
+    lost_o = isinstance(w, str) or not all(np.isfinite(w[k]).all() for k in ('b_basin', 'b_north', 'bs_ml') if k in w)
+    if lost_o or lost_k:
+      # a blow-up is preceded by a noisy state: the step at which each side gives up may differ, the fact may not
+      assert undefined or (lost_o and lost_k), '%s member %d: lost by %s only (status %d, oracle %s)' % (
+          workload, m, 'the oracle' if lost_o else 'the kernel', st[i], w if isinstance(w, str) else 'finite')
+      rep['lost_by_both'] += int(lost_o and lost_k)
+      continue
+    err = max(relmax(got[k][i], w[k]) for k in LATTICE_FIELDS if k in got and k in w)
+    if undefined:
+      rep['flagged_matching' if err < tol else 'flagged_missing'] += 1
+    else:
+      rep['worst_unflagged'] = max(rep['worst_unflagged'], err)
+      assert err < tol, '%s lattice member %d (status %d): rel err %.3e after %d steps, not flagged' % (
+          workload, m, st[i], err, nsteps)
+  nflag = rep['census']['parity_undefined']
+  rep['flagged_fraction'] = nflag / len(ms)
+  assert rep['flagged_fraction'] <= max_flagged, '%s: %d of %d sampled members carry a parity-undefined bit' % (
+      workload, nflag, len(ms))
+  return rep

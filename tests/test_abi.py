@@ -55,3 +55,26 @@ def test_no_cpu_fallback():
   from pymoc_b200.ensemble import Ensemble
   with pytest.raises(RuntimeError, match='no CUDA device'):
     Ensemble(configs.c1_timestepping(1))
+
+
+def test_spec_rejects_arrays_that_are_neither_shared_nor_per_member():
+  """a per-member array whose leading dimension is neither 1 nor M would be read out of bounds
+  on the device; ModelSpec refuses it (e.g. tau on the ny-point grid passed 1-D, kappa variants passed 2-D)."""
+  import numpy as np
+  import pytest
+
+  from pymoc_b200 import configs
+  from pymoc_b200.spec import ChannelSpec, ColumnSpec, ModelSpec
+  good = configs.c2_column_so(8, ntau=4)
+  z, y = good.z, good.so.y
+  col = ColumnSpec.build(z, np.full((8, z.size), 2e-5), 6e13, 0.03, 0.03 * np.exp(z / 300.))
+  with pytest.raises(ValueError, match='so.tau'):  # tau on y as a bare [ny] array: ny != M
+    ModelSpec(M=8, z=z, dt=good.dt, K=good.K, basin=col, so=ChannelSpec.build(y, good.so.bs[:1], np.linspace(.1, .2, y.size)))
+  with pytest.raises(ValueError, match='basin.kappa'):  # [nvar=2, nz] read as [M=2, nz] but M == 8
+    ModelSpec(M=8, z=z, dt=good.dt, K=good.K, basin=ColumnSpec.build(z, np.full((2, z.size), 2e-5), 6e13, 0.03, 0.0 * z),
+              so=good.so)
+  with pytest.raises(ValueError, match='basin.bs'):
+    ModelSpec(M=8, z=z, dt=good.dt, K=good.K, basin=ColumnSpec.build(z, 2e-5, 6e13, np.full(3, 0.03), 0.0 * z), so=good.so)
+  # the shared / per-member forms pass
+  ModelSpec(M=8, z=z, dt=good.dt, K=good.K, basin=col,
+            so=ChannelSpec.build(y, good.so.bs[:1], np.linspace(.1, .2, y.size)[None, :]))

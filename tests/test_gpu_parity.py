@@ -170,3 +170,27 @@ def test_jn_and_wide_split_launches_bitwise(cuda):
 
 def test_edge_sizes_vs_live_oracle(cuda):
   print('edge sizes: worst relative error %.2e' % edge_sizes(cuda, wide=True))
+
+
+# Bench-lattice samples: seeded-random members of the very lattices bench.py steps,
+# every one against the live oracle; see parity_common.lattice_sample for the contract.
+@pytest.mark.parametrize('workload,M,nsample,nsteps,tol,max_flagged', [
+    ('C1', 16384, 64, 600, TOL, 0.02),
+    ('C2', 65536, 256, 600, TOL, 0.02),
+    ('C3', 262144, 256, 600, TOL, 0.02),
+    ('twobasin', 32768, 256, 600, TOL, 0.02),
+    ('C4', 32768, 256, 600, TOL, 0.10),
+    ('C5', 32768, 256, 600, TOL, 0.02),
+    ('C3_bvp', 262144, 32, 2400, 1e-5, 0.02),  # the literal script (F2010 smoother): stated tolerance, 100 refreshes
+])
+def test_bench_lattice_sample_vs_live_oracle(cuda, workload, M, nsample, nsteps, tol, max_flagged):
+  from parity_common import lattice_sample
+  rep = lattice_sample(cuda, workload, M, nsample, nsteps, seed=20261018, tol=tol, max_flagged=max_flagged)
+  print('lattice sample %s' % rep)
+
+
+def test_c4_lattice_long_run(cuda):
+  """C4 at the bench's own length (2 400 steps: steady state, where the no-flux bottom ties develop)."""
+  from parity_common import lattice_sample
+  rep = lattice_sample(cuda, 'C4', 32768, 64, 2400, seed=4, max_flagged=0.15)
+  print('lattice sample %s' % rep)
