@@ -62,11 +62,11 @@ typedef struct {
                                      order, parity for this member is undefined */
 #define PMOC_ST_ML_INDEX 16u      /* SO_ML needed np.argwhere(Psi_b > 0)[0][0] / np.nonzero(Psi_b)[0][0] of an
                                      all-non-positive / all-zero Psi_b: the reference raises IndexError */
-#define PMOC_ST_TIE_CELL 128u     /* isopycnal remap (psi_thermwind.py:177-184): a cell carrying transport has end
-                                     points within 4 eps of each other (flat, or one rounding from flat / inverted).
-                                     Psib's clip((top-x)/(top-bot), 0, 1) jumps by the cell's whole transport between
-                                     "flat" and "inverted by one ulp", so the reference's own answer is decided by the
-                                     last bit of its state there (structural in the 'jn' loop, whose no-flux bottom
+#define PMOC_ST_TIE_CELL 128u     /* isopycnal remap (psi_thermwind.py:177-184): a cell carrying transport is inverted
+                                     by no more than 4 eps (relative), or is the bottom cell within 4 eps of flat.  Psib's
+                                     clip((top-x)/(top-bot), 0, 1) jumps by the cell's whole transport between "flat"
+                                     and "inverted by one ulp", so the reference's own answer is decided by the last
+                                     bit of its state there (structural in the 'jn' loop, whose no-flux bottom
                                      condition bbot = b[1] drives b[0] - b[1] to zero); parity is undefined unless
                                      the roundings happen to agree */
 #define PMOC_ST_BS_SAWTOOTH 256u  /* (informational, implies BS_NONMONOTONE) bs(y) decreases on >= 3 segments north of

@@ -471,13 +471,20 @@ PM_COLD double remap_flat_fix(double c, double x, int k, int nz, const double* b
   return c;
 }
 
-// A cell whose end points are within 4 eps (relative) of each other while it carries transport: between "flat"
-// ((top-x)/0 = +-inf -> the cell's transport goes to the classes below it) and "inverted by one ulp"
-// ((top-x)/(-ulp) -> to the classes above it) psib jumps by the whole u_c, so the last bit of the state decides.
+// PMOC_ST_TIE_CELL.  Psib's clip((top-x)/(top-bot), 0, 1) sends a cell's transport u_c to the classes BELOW it when
+// the cell is upright or flat ((top-x)/0 = +-inf) and to the classes ABOVE it when it is inverted, so between
+// "flat" and "inverted by one ulp" psib jumps by the whole u_c: there the last bit of the state decides.  Flagged:
+//   * a cell that IS inverted, by no more than 4 eps (relative, i.e. 4..8 ulp): one rounding away from flat;
+//   * the bottom cell within 4 eps of flat, either way: under the 'jn' no-flux condition bbot = b[1] its two
+//     levels are the same number one step apart in time, so their difference is the last increment of b[1] --
+//     of either sign, and at rounding level once the bottom has equilibrated.
+// Not flagged: interior cells that are upright by a few ulp.  Those are the rounded steady state of a column
+// relaxing onto bs from below (levels 4, 3, 2, 1 ulp apart); the upwind step is monotone, neither arithmetic
+// inverts them, and upright and flat cells contribute identically.
 constexpr double kTieEps = 4.0 * 2.220446049250313e-16;
-PM_DEV bool remap_tie(double bot, double top, double u) {
-  const double a = fabs(top), b = fabs(bot);
-  return u != 0.0 && fabs(top - bot) <= kTieEps * (a > b ? a : b);
+PM_DEV bool remap_tie(double bot, double top, double u, bool bottom) {
+  const double a = fabs(top), b = fabs(bot), gap = top - bot;
+  return u != 0.0 && fabs(gap) <= kTieEps * (a > b ? a : b) && (gap < 0.0 || bottom);
 }
 
 template <int LPL>
@@ -555,7 +562,7 @@ PM_DEV BGrid tw_psib(const double (&psi)[LPL], const double (&b1)[LPL], const do
       const double mu = from2 ? (last ? m2n : m2[jn]) : (last ? m1n : m1[jn]);
       const double upv = from2 ? up2[j] : up1[j];
       const double mb = from2 ? m2[j] : m1[j], bv = from2 ? b2[j] : b1[j];
-      tie |= remap_tie(bv, upv, u[j]);
+      tie |= remap_tie(bv, upv, u[j], i == 0);
       if (allexc || mu != upv || mb != bv) {
         excm |= 1u << j;
         ++ne;

@@ -182,7 +182,7 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
     if (i < nz - 1) {
       const double u = -(P[i + 1] - P[i]);
       unsorted |= !(b1[i + 1] >= b1[i]) || !(b2[i + 1] >= b2[i]) || u != u;
-      if (u < 0 ? pm::remap_tie(b2[i], b2[i + 1], u) : pm::remap_tie(b1[i], b1[i + 1], u)) status |= PMOC_ST_TIE_CELL;
+      if (u < 0 ? pm::remap_tie(b2[i], b2[i + 1], u, i == 0) : pm::remap_tie(b1[i], b1[i + 1], u, i == 0)) status |= PMOC_ST_TIE_CELL;
     }
   }
   lo = rt::wmin(lo);
