@@ -46,7 +46,7 @@ struct SmemPlan {
   int off_warp0, per_warp;                                          // per warp region
   int w_col[3];                                                     // column tables of basin / north / pac (3 or 4 nzp each)
   int col_tables;                                                   // 0: folded coefficients are built from global memory
-  int w_remap, w_psib, w_cnt, w_bs, w_sinv, w_tau, w_bvp;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
+  int w_remap, w_psib, w_cnt, w_bs, w_sinv, w_tau;  // w_remap: 6*nzp of remap scratch, w_psib: psib[nb]
   int w_nweff[2], w_bb, w_pm, w_scan;                               // SO_ML / 'jn' order
   PM_HD size_t bytes(int wpb) const { return sizeof(double) * (size_t)(off_warp0 + per_warp * wpb); }
 };
@@ -105,7 +105,6 @@ static PM_HD SmemPlan plan_smem(int LPL, int ny, int nb, unsigned flags) {
     s.w_bs = w; w += s.nyp;
     s.w_sinv = w; w += s.nyp;
     s.w_tau = w; w += s.nyp;
-    if (flags & PMOC_SO_BVP) { s.w_bvp = w; w += 4 * s.nzp; }
   }
   if (exact) {
     // the remap scratch (6*nzp + nb, live only inside a refresh) overlays the per-step arrays,

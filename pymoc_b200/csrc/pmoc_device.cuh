@@ -866,7 +866,6 @@ struct SoPar {
   const double* tau_y;                           // tau on the y grid (shared memory) or nullptr for a float tau
   double c;                                      // F2010 phase speed (BVP branch only)
   int with_Ek;
-  double* bvp_s;                                 // 4*nzp doubles of scratch (BVP branch only)
 };
 struct SoSurf {  // per-refresh scan of bs(y)
   double mn, bsN, y0, yN;
@@ -963,20 +962,108 @@ PM_COLD double tau_mean100(double y0, double yN, const double* ygrid, const doub
 //   u(h) = A u(0) + B u'(0),  u'(h) = C u(0) + D u'(0),  A D - B C = 1.
 // With t_k = a_k h^k the recurrence is t_{k+2} = (Q0 t_k + Q1 t_{k-1}) / ((k+2)(k+1)),
 // Q0 = q0 h^2, Q1 = q1 h^3; Bh = B/h.  All terms are positive for a stable stratification.
-template <int LPL>
-PM_DEV bool cell_propagators(const double (&Q0)[LPL], const double (&Q1)[LPL], double (&A)[LPL], double (&Bh)[LPL],
-                             double (&D)[LPL]) {
-  double am[LPL], ak[LPL], an[LPL], bm[LPL], bk[LPL], bn[LPL];
+//
+// The trip count is fixed per call from Qmax = max over the warp of |Q0| + |Q1| (every term is bounded by
+// Qmax^(k/2) / k!): the smallest multiple of three after which the tail is below 1e-18 of the sums, looked up in
+// kSeriesQ.  No convergence test, no divide (1/((k+2)(k+1)) is tabulated) and no register moves (three terms per
+// trip rotate through three registers) inside the loop: 9 FP64 instructions per term and level.
+#ifdef PMOC_EMU
+#define PM_CONST static const
+#else
+#define PM_CONST static __constant__
+#endif
+constexpr int kSeriesMax = 99;  // terms tabulated
+PM_CONST double kSeriesInv[kSeriesMax] = {
+    0.5, 0.16666666666666666, 0.083333333333333329, 0.050000000000000003,
+    0.033333333333333333, 0.023809523809523808, 0.017857142857142856, 0.013888888888888888,
+    0.011111111111111112, 0.0090909090909090905, 0.007575757575757576, 0.00641025641025641,
+    0.0054945054945054949, 0.0047619047619047623, 0.0041666666666666666, 0.0036764705882352941,
+    0.0032679738562091504, 0.0029239766081871343, 0.002631578947368421, 0.0023809523809523812,
+    0.0021645021645021645, 0.001976284584980237, 0.0018115942028985507, 0.0016666666666666668,
+    0.0015384615384615385, 0.0014245014245014246, 0.0013227513227513227, 0.0012315270935960591,
+    0.0011494252873563218, 0.0010752688172043011, 0.0010080645161290322, 0.000946969696969697,
+    0.00089126559714795004, 0.00084033613445378156, 0.00079365079365079365, 0.00075075075075075074,
+    0.00071123755334281653, 0.00067476383265856947, 0.00064102564102564103, 0.00060975609756097561,
+    0.00058072009291521487, 0.00055370985603543741, 0.00052854122621564484, 0.00050505050505050505,
+    0.00048309178743961351, 0.00046253469010175765, 0.00044326241134751772, 0.00042517006802721087,
+    0.00040816326530612246, 0.00039215686274509802, 0.00037707390648567121, 0.00036284470246734398,
+    0.00034940600978336826, 0.00033670033670033672, 0.00032467532467532468, 0.00031328320802005011,
+    0.00030248033877797946, 0.00029222676797194621, 0.0002824858757062147, 0.00027322404371584699,
+    0.00026441036488630354, 0.00025601638504864311, 0.000248015873015873, 0.0002403846153846154,
+    0.0002331002331002331, 0.00022614201718679331, 0.00021949078138718174, 0.00021312872975277067,
+    0.00020703933747412008, 0.00020120724346076458, 0.00019561815336463224, 0.00019025875190258751,
+    0.00018511662347278786, 0.00018018018018018018, 0.00017543859649122806, 0.00017088174982911826,
+    0.0001665001665001665, 0.00016228497241155469, 0.00015822784810126583, 0.00015432098765432098,
+    0.00015055706112616682, 0.00014692918013517486, 0.00014343086632243257, 0.00014005602240896358,
+    0.00013679890560875513, 0.00013365410318096765, 0.00013061650992685477, 0.00012768130745658836,
+    0.00012484394506866417, 0.0001221001221001221, 0.00011944577161968466, 0.0001168770453482936,
+    0.00011439029970258523, 0.00011198208286674133, 0.00010964912280701755, 0.00010738831615120275,
+    0.00010519671786240269, 0.00010307153164296021, 0.00010101010101010101,
+};
+constexpr int kSeriesSteps = 32;  // trip counts 6, 9, ..., 99
+PM_CONST double kSeriesQ[kSeriesSteps] = {  // largest Qmax each trip count serves
+    0.00021189593823687914, 0.0071126781656659097, 0.05976755391215325, 0.25608636817847191,
+    0.7486299437050602, 1.7217046228815054, 3.3689509837018066, 5.8782970176865499,
+    9.4238622023950125, 14.162597418420889, 20.233699163184948, 27.759474637795645,
+    36.846863341635874, 47.589171919205832, 60.067791043705142, 74.353784497096072,
+    90.509307286529619, 108.58884467139403, 128.64028121036503, 150.70581641647988,
+    174.82274590618601, 201.02412660661238, 229.33934305261795, 259.79458981808773,
+    292.41328307573838, 327.21641235557291, 364.22284185350316, 403.44956915011363,
+    444.91194792769073, 488.62388020105715, 534.59798267940118, 582.84573112698445,
+};
+
+// number of three-term trips for a given Qmax (warp-uniform), 0 when the table does not reach (Qmax > 583)
+PM_DEV int series_trips(double qmax) {
+  int n = 0;
+  for (int t = 0; t < kSeriesSteps; ++t)
+    if (n == 0 && qmax <= kSeriesQ[t]) n = t + 2;
+  return (qmax == qmax) ? n : 0;
+}
+
+template <int JC>
+PM_DEV void cell_propagators_chunk(const double* Q0, const double* Q1, double* A, double* Bh, double* D, int trips) {
+  double ax[JC], ay[JC], az[JC], bx[JC], by[JC], bz[JC], sa[JC], sb[JC], sd[JC], q0[JC], q1[JC];
   PM_UNROLL
+  for (int j = 0; j < JC; ++j) {
+    q0[j] = Q0[j]; q1[j] = Q1[j];
+    ax[j] = 0.; ay[j] = 1.; az[j] = 0.;  // a-series: t_-1, t_0, t_1
+    bx[j] = 0.; by[j] = 0.; bz[j] = 1.;  // b-series
+    sa[j] = 1.; sb[j] = 1.; sd[j] = 1.;
+  }
+  for (int g = 0; g < trips; ++g) {
+    const int k = 3 * g;
+    const double i0 = kSeriesInv[k], i1 = kSeriesInv[k + 1], i2 = kSeriesInv[k + 2];
+    const double c0 = (double)(k + 2), c1 = (double)(k + 3), c2 = (double)(k + 4);
+    PM_UNROLL
+    for (int j = 0; j < JC; ++j) {
+      ax[j] = rt::fma(q0[j], ay[j], q1[j] * ax[j]) * i0;  // t_{k+2} from t_k (y), t_{k-1} (x)
+      bx[j] = rt::fma(q0[j], by[j], q1[j] * bx[j]) * i0;
+      sa[j] = sa[j] + ax[j]; sb[j] = sb[j] + bx[j]; sd[j] = rt::fma(c0, bx[j], sd[j]);
+      ay[j] = rt::fma(q0[j], az[j], q1[j] * ay[j]) * i1;  // t_{k+3} from t_{k+1} (z), t_k (y)
+      by[j] = rt::fma(q0[j], bz[j], q1[j] * by[j]) * i1;
+      sa[j] = sa[j] + ay[j]; sb[j] = sb[j] + by[j]; sd[j] = rt::fma(c1, by[j], sd[j]);
+      az[j] = rt::fma(q0[j], ax[j], q1[j] * az[j]) * i2;  // t_{k+4} from t_{k+2} (x), t_{k+1} (z)
+      bz[j] = rt::fma(q0[j], bx[j], q1[j] * bz[j]) * i2;
+      sa[j] = sa[j] + az[j]; sb[j] = sb[j] + bz[j]; sd[j] = rt::fma(c2, bz[j], sd[j]);
+    }
+  }
+  PM_UNROLL
+  for (int j = 0; j < JC; ++j) { A[j] = sa[j]; Bh[j] = sb[j]; D[j] = sd[j]; }
+}
+
+// the adaptive form (term-by-term convergence test), for cells beyond the table: N2 h^2 / c^2 > 583
+template <int LPL>
+PM_COLD bool cell_propagators_adaptive(const double (&Q0)[LPL], const double (&Q1)[LPL], double (&A)[LPL],
+                                       double (&Bh)[LPL], double (&D)[LPL]) {
+  double am[LPL], ak[LPL], an[LPL], bm[LPL], bk[LPL], bn[LPL];
   for (int j = 0; j < LPL; ++j) {
     am[j] = 0.; ak[j] = 1.; an[j] = 0.;
     bm[j] = 0.; bk[j] = 0.; bn[j] = 1.;
     A[j] = 1.; Bh[j] = 1.; D[j] = 1.;
   }
-  for (int k = 0; k < 600; ++k) {
+  for (int k = 0; k < 2000; ++k) {
     const double inv = rt::div_normal(1.0, (double)(k + 2) * (double)(k + 1)), kk = (double)(k + 2);
     bool big = false;
-    PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
       const double na = (Q0[j] * ak[j] + Q1[j] * am[j]) * inv;
       const double nb = (Q0[j] * bk[j] + Q1[j] * bm[j]) * inv;
@@ -993,99 +1080,158 @@ PM_DEV bool cell_propagators(const double (&Q0)[LPL], const double (&Q1)[LPL], d
   return false;
 }
 
+template <int LPL>
+PM_DEV bool cell_propagators(const double (&Q0)[LPL], const double (&Q1)[LPL], double (&A)[LPL], double (&Bh)[LPL],
+                             double (&D)[LPL]) {
+  double qm = 0.0;
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const double q = fabs(Q0[j]) + fabs(Q1[j]);
+    qm = (q > qm || q != q) ? q : qm;
+  }
+  qm = rt::wmax(qm);
+  const int trips = series_trips(qm);
+  if (trips == 0) return cell_propagators_adaptive<LPL>(Q0, Q1, A, Bh, D);
+  // levels in chunks of at most four: 11 live doubles per level
+  constexpr int JC = LPL <= 4 ? LPL : (LPL + 1) / 2;
+  cell_propagators_chunk<JC>(Q0, Q1, A, Bh, D, trips);
+  if constexpr (JC < LPL) cell_propagators_chunk<LPL - JC>(Q0 + JC, Q1 + JC, A + JC, Bh + JC, D + JC, trips);
+  return true;
+}
+
 // F2010 smoother of Psi_GM (psi_SO.py:308-323): y'' = N2(z)/c^2 (y - T(z)), Dirichlet ends.
 // N2 and T are piecewise linear on z (np.interp closures), so with u = y - T each cell obeys
 // u'' = q(s) u exactly; matching y' at the nodes gives a symmetric tridiagonal system for the
 // nodal values.  This is the converged solution of the ODE the reference hands to its
-// adaptive, tol=1e-3 solve_bvp (stated tolerance 1e-5).
+// adaptive, tol=1e-3 solve_bvp (stated tolerance 1e-5), so nothing here
+// is tied to the reference's operation order: reciprocals and fused multiply-adds throughout.
+//
+// The tridiagonal system (rows = levels, LPL per lane) is solved by partitioning: every lane eliminates
+// its first LPL-1 rows against the last unknown of the lane below (X_prev) and its own last unknown (X),
+//   x_j = y_j - v_j X_prev - w_j X,
+// its last row then couples X_prev, X and X_next only: a 32-row tridiagonal system, one row per lane,
+// solved by parallel cyclic reduction (five shuffle rounds); the interior unknowns follow.  The system is
+// a symmetric M-matrix (diagonally dominant: A, D >= 1), so are its Schur complements: no pivoting.
 // In/out: g holds T on entry and the solution y on return (m^3/s).
 template <int LPL>
 PM_DEV void so_bvp(double (&g)[LPL], const double (&b)[LPL], double c, double ya, double yb, const double* zs, int nz,
-                   double* scratch, unsigned* status) {
-  const int nzp = 32 * LPL;
-  double *lo_s = scratch, *di_s = scratch + nzp, *up_s = scratch + 2 * nzp, *rh_s = scratch + 3 * nzp;
-  const double c2 = c * c;
+                   unsigned* status) {
+  static_assert(LPL >= 2, "partitioned solve: at least two levels per lane");
+  const int Ln = rt::lane();
+  const double rc2 = rt::div_normal(1.0, c * c);
   // N2 (psi_SO.py:154-160) at the own levels and at the level above
   const double bnext = rt::shfl_down(b[0], 1), bprev = rt::shfl_up(b[LPL - 1], 1);
-  double n2[LPL];
+  double n2[LPL], h[LPL], rh[LPL];
+  PM_UNROLL
+  for (int j = 0; j < LPL; ++j) {
+    const int i = lev<LPL>(j);
+    h[j] = i < nz - 1 ? zs[i + 1] - zs[i] : 1.0;
+    rh[j] = rt::div_normal(1.0, h[j]);
+  }
+  const double rh_p = rt::shfl_up(rh[LPL - 1], 1), h_p = rt::shfl_up(h[LPL - 1], 1);
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
     const double up = j < LPL - 1 ? b[j + 1 < LPL ? j + 1 : j] : bnext;
     const double dn = j > 0 ? b[j > 0 ? j - 1 : 0] : bprev;
+    const double hd = j > 0 ? h[j > 0 ? j - 1 : 0] : h_p, rhd = j > 0 ? rh[j > 0 ? j - 1 : 0] : rh_p;
     double v = 0.0;
     if (i < nz) {
       if (i == 0)
-        v = (up - b[j]) / (zs[1] - zs[0]);
+        v = (up - b[j]) * rh[j];
       else if (i == nz - 1)
-        v = (b[j] - dn) / (zs[i] - zs[i - 1]);
+        v = (b[j] - dn) * rhd;
       else
-        v = (up - dn) / ((zs[i + 1] - zs[i]) + (zs[i] - zs[i - 1]));
+        v = rt::div_normal(up - dn, h[j] + hd);
     }
     n2[j] = v;
   }
   const double n2next = rt::shfl_down(n2[0], 1), gnext = rt::shfl_down(g[0], 1);
-  double Q0[LPL], Q1[LPL], h[LPL], Tp[LPL], A[LPL], Bh[LPL], D[LPL];
+  double Q0[LPL], Q1[LPL], Tp[LPL], A[LPL], Bh[LPL], D[LPL];
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
     const bool cell = i < nz - 1;
-    h[j] = cell ? zs[i + 1] - zs[i] : 1.0;
     const double n2u = j < LPL - 1 ? n2[j + 1 < LPL ? j + 1 : j] : n2next;
     const double gu = j < LPL - 1 ? g[j + 1 < LPL ? j + 1 : j] : gnext;
-    Q0[j] = cell ? n2[j] / c2 * h[j] * h[j] : 0.0;
-    Q1[j] = cell ? (n2u - n2[j]) / c2 * h[j] * h[j] : 0.0;  // slope * h^3
-    Tp[j] = cell ? (gu - g[j]) / h[j] : 0.0;
+    const double s = rc2 * (h[j] * h[j]);
+    Q0[j] = cell ? n2[j] * s : 0.0;
+    Q1[j] = cell ? (n2u - n2[j]) * s : 0.0;  // slope * h^3
+    Tp[j] = cell ? (gu - g[j]) * rh[j] : 0.0;
   }
   if (!cell_propagators<LPL>(Q0, Q1, A, Bh, D)) *status |= 32u;
   double ib[LPL];
   PM_UNROLL
-  for (int j = 0; j < LPL; ++j) ib[j] = rt::div_normal(1.0, h[j] * Bh[j]);  // h > 0, Bh >= 1
+  for (int j = 0; j < LPL; ++j) ib[j] = rt::div_normal(rh[j], Bh[j]);  // 1 / (h Bh): h > 0, Bh >= 1
   const double ib_p = rt::shfl_up(ib[LPL - 1], 1), D_p = rt::shfl_up(D[LPL - 1], 1), Tp_p = rt::shfl_up(Tp[LPL - 1], 1);
+  // rows: lo x_{i-1} + di x_i + up x_{i+1} = r (identity rows at the two ends and in the padding)
+  double lo[LPL], di[LPL], up[LPL], r[LPL];
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {
     const int i = lev<LPL>(j);
-    if (i < nz) {
-      double lo = 0., di = 1., up = 0., rh;
-      if (i == 0)
-        rh = ya - g[j];
-      else if (i == nz - 1)
-        rh = yb - g[j];
-      else {
-        const double ibm = j > 0 ? ib[j > 0 ? j - 1 : 0] : ib_p, Dm = j > 0 ? D[j > 0 ? j - 1 : 0] : D_p;
-        const double Tpm = j > 0 ? Tp[j > 0 ? j - 1 : 0] : Tp_p;
-        lo = -ibm;
-        up = -ib[j];
-        di = Dm * ibm + A[j] * ib[j];
-        rh = Tp[j] - Tpm;
-      }
-      lo_s[i] = lo; di_s[i] = di; up_s[i] = up; rh_s[i] = rh;
+    lo[j] = 0.; di[j] = 1.; up[j] = 0.; r[j] = 0.;
+    if (i == 0)
+      r[j] = ya - g[j];
+    else if (i == nz - 1)
+      r[j] = yb - g[j];
+    else if (i < nz) {
+      const double ibm = j > 0 ? ib[j > 0 ? j - 1 : 0] : ib_p, Dm = j > 0 ? D[j > 0 ? j - 1 : 0] : D_p;
+      const double Tpm = j > 0 ? Tp[j > 0 ? j - 1 : 0] : Tp_p;
+      lo[j] = -ibm;
+      up[j] = -ib[j];
+      di[j] = rt::fma(Dm, ibm, A[j] * ib[j]);
+      r[j] = Tp[j] - Tpm;
     }
   }
-  rt::syncwarp();
-  // Thomas sweep (every lane runs it, lane 0 stores)
+  // interior rows 0 .. LPL-2 of the lane: Thomas with three right-hand sides (r, lo[0] e_first, up[n-1] e_last)
+  constexpr int n = LPL - 1;
+  double cp[n], y[n], v[n], w[n];
   {
-    const bool w = rt::lane() == 0;
-    double cp = 0., dp = 0.;
-    for (int i = 0; i < nz; ++i) {
-      const double l = lo_s[i], r = rt::div_normal(1.0, di_s[i] - l * cp);  // diagonally dominant: pivots > 0
-      cp = up_s[i] * r;
-      dp = (rh_s[i] - l * dp) * r;
-      if (w) { up_s[i] = cp; rh_s[i] = dp; }
+    double pc = 0., py = 0., pv = 0.;
+    PM_UNROLL
+    for (int j = 0; j < n; ++j) {
+      const double m = rt::div_normal(1.0, rt::fma(-lo[j], pc, di[j]));
+      pc = up[j] * m;
+      py = rt::fma(-lo[j], py, r[j]) * m;
+      pv = (j == 0 ? lo[0] : -lo[j] * pv) * m;
+      cp[j] = pc; y[j] = py; v[j] = pv;
     }
-    double x = 0.;
-    for (int i = nz - 1; i >= 0; --i) {
-      x = rh_s[i] - up_s[i] * x;
-      if (w) di_s[i] = x;
+    // back substitution; w: the right-hand side up[n-1] e_last has forward image e_last * cp[n-1]
+    w[n - 1] = cp[n - 1];
+    PM_UNROLL
+    for (int j = n - 2; j >= 0; --j) {
+      y[j] = rt::fma(-cp[j], y[j + 1], y[j]);
+      v[j] = rt::fma(-cp[j], v[j + 1], v[j]);
+      w[j] = -cp[j] * w[j + 1];
     }
   }
-  rt::syncwarp();
+  // interface row of the lane: a X_prev + bb X + cc X_next = d
+  const double y0n = rt::shfl_down(y[0], 1), v0n = rt::shfl_down(v[0], 1), w0n = rt::shfl_down(w[0], 1);
+  const double lol = lo[LPL - 1], upl = Ln < 31 ? up[LPL - 1] : 0.0;
+  double a = -lol * v[n - 1];
+  double bb = rt::fma(-upl, v0n, rt::fma(-lol, w[n - 1], di[LPL - 1]));
+  double cc = -upl * w0n;
+  double d = rt::fma(-upl, y0n, rt::fma(-lol, y[n - 1], r[LPL - 1]));
   PM_UNROLL
-  for (int j = 0; j < LPL; ++j) {
-    const int i = lev<LPL>(j);
-    if (i < nz) g[j] = g[j] + di_s[i];
+  for (int sft = 1; sft < 32; sft <<= 1) {  // parallel cyclic reduction
+    const double am = rt::shfl_up(a, sft), bm = rt::shfl_up(bb, sft), cm = rt::shfl_up(cc, sft), dm = rt::shfl_up(d, sft);
+    const double ap = rt::shfl_down(a, sft), bp = rt::shfl_down(bb, sft), cq = rt::shfl_down(cc, sft),
+                 dp = rt::shfl_down(d, sft);
+    const bool hm = Ln >= sft, hp = Ln + sft < 32;
+    const double al = hm ? -a * rt::div_normal(1.0, bm) : 0.0, ga = hp ? -cc * rt::div_normal(1.0, bp) : 0.0;
+    bb = rt::fma(ga, ap, rt::fma(al, cm, bb));
+    d = rt::fma(ga, dp, rt::fma(al, dm, d));
+    a = al * am;
+    cc = ga * cq;
   }
-  rt::syncwarp();
+  const double X = d * rt::div_normal(1.0, bb);
+  double Xp = rt::shfl_up(X, 1);
+  if (Ln == 0) Xp = 0.0;
+  PM_UNROLL
+  for (int j = 0; j < n; ++j) {
+    if (lev<LPL>(j) < nz) g[j] = g[j] + rt::fma(-w[j], X, rt::fma(-v[j], Xp, y[j]));
+  }
+  if (lev<LPL>(LPL - 1) < nz) g[LPL - 1] = g[LPL - 1] + X;
 }
 
 // ys(b) for all levels of the lane at once when bs(y) is non-decreasing north of its minimum
@@ -1180,7 +1326,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
     const double z = zs[i < nz ? i : nz - 1];
     double g;
     if (BVP) {
-      g = qdiv(P.KGM * z, dy) * P.L * P.toptap[s] * P.bottap[s];
+      g = rt::div_normal(P.KGM * z, dy) * P.L * P.toptap[s] * P.bottap[s];  // dy >= 0.1
     } else {
       const double sl = rt::div_normal(z, dy), ms = -P.smax;  // dy >= 0.1, |z| <= H: in range
       const double mx = (sl >= ms || sl != sl) ? sl : ms;
@@ -1198,7 +1344,7 @@ PM_DEV void so_solve(double (&psi)[LPL], double (&ek)[LPL], double (&gm)[LPL], d
       ya = -(get_level<LPL>(ek, 0) * 1e6);
       yb = -(get_level<LPL>(ek, nz - 1) * 1e6);
     }
-    so_bvp<LPL>(gm, b, P.c, ya, yb, zs, nz, P.bvp_s, status);
+    so_bvp<LPL>(gm, b, P.c, ya, yb, zs, nz, status);
   }
   PM_UNROLL
   for (int j = 0; j < LPL; ++j) {

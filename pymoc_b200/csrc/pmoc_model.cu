@@ -109,7 +109,6 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
     }
     so.c = BVP ? vat(M.so_c, m) : 0.0;
     so.with_Ek = M.so_bvp_with_Ek;
-    so.bvp_s = BVP ? ws + sp.w_bvp : nullptr;
     so.f = vat(M.so_f, m); so.rho = vat(M.so_rho, m); so.L = vat(M.so_L, m);
     so.KGM = vat(M.so_KGM, m); so.smax = vat(M.so_smax, m);
     so.sill = sm + sp.off_tap; so.ektap = so.sill + sp.nzp; so.toptap = so.sill + 2 * sp.nzp;

@@ -113,7 +113,7 @@ PM_GLOBAL void k_so(SoArgs a) {
   double* zs = rt::smem();
   double* ysm = zs + a.nzp + 4;
   double* tap = ysm + a.nyp;
-  double* bss = tap + 4 * a.nzp + (size_t)(3 * a.nyp + (BVP ? 4 * a.nzp : 0)) * W;
+  double* bss = tap + 4 * a.nzp + (size_t)(3 * a.nyp) * W;
   double* sinv = bss + a.nyp;
   double* tau_s = sinv + a.nyp;
   for (int i = W * 32 + L; i < a.nzp + 4; i += nthr) zs[i] = M.z[i < nz ? i : nz - 1];
@@ -139,7 +139,6 @@ PM_GLOBAL void k_so(SoArgs a) {
   so.sill = tap; so.ektap = tap + a.nzp; so.toptap = tap + 2 * a.nzp; so.bottap = tap + 3 * a.nzp;
   so.c = BVP ? vat(M.so_c, m) : 0.0;
   so.with_Ek = M.so_bvp_with_Ek;
-  so.bvp_s = tau_s + a.nyp;
   double b[LPL], psi[LPL], ek[LPL], gm[LPL], ysv[LPL];
   pm::load_lev<LPL>(b, vrow(a.b, m), nz, 0.0);
   unsigned status = 0;
@@ -397,7 +396,7 @@ int pmoc_so_solve(const pmoc_model* so, pmoc_vec b, pmoc_vec bs, double* Psi, do
   PM_DISPATCH_LPL(so->nz, {
     a.nzp = 32 * LPL;
     const size_t smem =
-        sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + 4 * a.nzp + (3 * a.nyp + (bvp ? 4 * a.nzp : 0)) * kWarpsPerBlock);
+        sizeof(double) * (size_t)(a.nzp + 4 + a.nyp + 4 * a.nzp + 3 * a.nyp * kWarpsPerBlock);
     if (bvp) return launch(k_so<LPL, true>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
     return launch(k_so<LPL, false>, blocks_for(so->M), 32 * kWarpsPerBlock, smem, stream, a);
   });

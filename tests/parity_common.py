@@ -1,4 +1,7 @@
 """Parity checks shared by the CPU (warp-emulator) and GPU (C ABI on cuda:0) test files."""
+import json
+import os
+
 import numpy as np
 
 from helpers import golden, relmax, spec_from_cases
@@ -195,6 +198,56 @@ def lattice_sample(backend, workload, M, nsample, nsteps, seed=0, tol=TOL, max_f
           workload, m, st[i], err, nsteps)
   nflag = rep['census']['parity_undefined']
   rep['flagged_fraction'] = nflag / len(ms)
+  path = os.environ.get('PMOC_LATTICE_REPORT')  # evidence file (one JSON line per sample), see profiles/
+  if path:
+    with open(path, 'a') as f:
+      f.write(json.dumps(dict(rep, backend=type(backend).__name__, tol=tol)) + '\n')
   assert rep['flagged_fraction'] <= max_flagged, '%s: %d of %d sampled members carry a parity-undefined bit' % (
       workload, nflag, len(ms))
   return rep
+
+
+def f2010_smoother_converged(backend, sizes=(46, 80, 200, 256), bvp_tol=1e-9, tol=2e-9):
+  """The F2010 smoother of Psi_GM (psi_SO.py:308-323) against scipy's solve_bvp run to a tight tolerance on a refined
+  mesh (the reference runs the same ODE at tol = 1e-3): the kernel's piecewise-exact solution (series propagators +
+  partitioned cyclic reduction) is the converged one (measured 6e-14 against tol = 1e-11, which takes scipy minutes).
+  Levels per lane 2, 3, 7, 8."""
+  import warnings
+
+  from scipy import integrate
+
+  from oracle import pymoc_oracle as O
+  from pymoc_b200 import configs
+  from pymoc_b200.spec import _vec
+  warnings.filterwarnings('ignore')
+  worst = 0.0
+  for nz in sizes:
+    if nz == 80:
+      spec = configs.c3_twocol_so(2, c=0.1, axes=(2, 1, 1, 1))
+    else:
+      spec = configs.c2_column_so(2, nz=nz, ntau=2)
+      spec.so.c, spec.so.bvp_with_Ek = _vec(0.1, 'c'), True
+    ens = Ensemble(spec, backend=backend)
+    ens.run(25 if nz == 80 else 3)  # a state off the initial condition
+    state = ens.state()
+    ens.set_state(**state)
+    ens.diagnose()
+    got = ens.diagnostics()
+    assert not got['status'].any()
+    for m in range(spec.M):
+      case = spec.member_case(m)
+      so, z, b = case['so'], case['z'], state['b_basin'][m]
+      p = O.ChannelParams(z, so['y'], so['tau'], **{k: so[k] for k in so if k not in ('y', 'tau', 'bs')})
+      ek = O.so_ekman(p, b, so['bs']) / 1e6
+      width = np.array([max(p.y[-1] - O.so_outcrop(bi, p.y, so['bs']), 0.1) for bi in b])
+      target, n2 = p.KGM * z / width * p.L, O.so_n2(z, b)
+      rhs = lambda x, s: np.vstack((s[1], np.interp(x, z, n2) / p.c**2. * (s[0] - np.interp(x, z, target))))
+      ends = lambda sa, sb: np.array([sa[0] + ek[0] * 1e6, sb[0] + ek[-1] * 1e6])
+      zz = np.unique(np.concatenate([z, 0.5 * (z[1:] + z[:-1])]))
+      res = integrate.solve_bvp(rhs, ends, zz, np.zeros((2, zz.size)), tol=bvp_tol, max_nodes=2000000)
+      gm = res.sol(z)[0] / 1e6
+      blocked = width > p.y[-1] - p.y[0]
+      gm[blocked] = np.maximum(gm[blocked], -ek[blocked])
+      worst = max(worst, relmax(got['Psi_GM'][m], gm))
+  assert worst < tol, worst
+  return worst

@@ -120,3 +120,8 @@ def test_tie_cell_member_is_flagged(emu):
   want = O.run_coupled(spec.member_case(0), 61, O.REFERENCE)
   err = relmax(got['Psi_iso_b'][0], want['Psi_iso_b'])
   assert got['status'][0] & _abi.ST_TIE_CELL, (int(got['status'][0]), err)  # (today it also misses: err ~ 3e-2)
+
+
+def test_f2010_smoother_is_the_converged_solution(emu):
+  from parity_common import f2010_smoother_converged
+  f2010_smoother_converged(emu, sizes=(46, 80), bvp_tol=1e-8, tol=1e-8)

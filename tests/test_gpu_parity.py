@@ -194,3 +194,8 @@ def test_c4_lattice_long_run(cuda):
   from parity_common import lattice_sample
   rep = lattice_sample(cuda, 'C4', 32768, 64, 2400, seed=4, max_flagged=0.15)
   print('lattice sample %s' % rep)
+
+
+def test_f2010_smoother_is_the_converged_solution(cuda):
+  from parity_common import f2010_smoother_converged
+  print('F2010 smoother vs solve_bvp(tol=1e-8): worst %.2e' % f2010_smoother_converged(cuda, bvp_tol=1e-8, tol=1e-8))
