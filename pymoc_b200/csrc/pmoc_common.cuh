@@ -142,6 +142,7 @@ struct RunArgs {
   SmemPlan sp;
   long long it0, nsteps;
   int diagnose_only;
+  int sync_refresh;  // CTA barrier before every diagnosis: the CTA's warps then run its long instruction stream together
 };
 
 // per-column registers

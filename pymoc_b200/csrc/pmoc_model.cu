@@ -328,6 +328,9 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
   bool wr = dg || ii == last_refresh;
   for (;;) {
     if (refresh_next) {
+#ifndef PMOC_EMU
+      if (a.sync_refresh) __syncthreads();  // (warps of members beyond M have exited: they do not count)
+#endif
       refresh(wr);
       refresh_next = false;
       if (dg) break;
@@ -453,6 +456,9 @@ int launch_model(const RunArgs& ra, void* stream) {
   int wpb = kWarpsPerBlock, best = resident(kWarpsPerBlock);  // four warps per CTA unless another split is better
   for (int w = 1; w <= cap; ++w)
     if (resident(w) > best) { best = resident(w); wpb = w; }
+  // the F2010 smoother's diagnosis is the longest instruction stream: eight warps per CTA share its fetches
+  // (with the barrier below) when that costs no residency.  Measured, C3_bvp: 4 warps 0.515, 8 warps 0.522.
+  if ((t & PMOC_SO_BVP) && !(t & PMOC_HAS_ML) && resident(8) == best) wpb = 8;
   if (best == 0) return fail(PMOC_EUNSUPPORTED, "model does not fit the shared memory of one SM");
   if (const char* e = std::getenv("PMOC_WPB")) {  // tuning knob: force the warps per CTA
     const int w = std::atoi(e);
@@ -461,8 +467,15 @@ int launch_model(const RunArgs& ra, void* stream) {
   const long long grid = (ra.m.M + wpb - 1) / wpb;
   const int block = 32 * wpb;
   const size_t smem = ra.sp.bytes(wpb);
+  // A CTA barrier in front of every diagnosis re-aligns the CTA's warps, which then walk its ~9 000-instruction
+  // stream (144 KB of code, against a 32 KB L1.5 instruction cache) together and share the fetches: ncu's
+  // no_instruction stall was 1.28 warps per issue cycle without it.  Measured: C3_bvp 0.473 -> 0.515, C3 0.715 ->
+  // 0.731, C4 0.253 -> 0.259; the single-column kernels (short diagnosis) lose 1.5 % and keep running free.
+  RunArgs ra2 = ra;
+  ra2.sync_refresh = (t & PMOC_ISO) != 0;
+  if (const char* e = std::getenv("PMOC_REFRESH_SYNC")) ra2.sync_refresh = std::atoi(e);
 #define PM_CASE(T) \
-  case (T): return launch(k_model<LPL, (T)>, grid, block, smem, stream, ra);
+  case (T): return launch(k_model<LPL, (T)>, grid, block, smem, stream, ra2);
   switch (t) {
     PM_CASE(PMOC_HAS_TW)
     PM_CASE(PMOC_HAS_SO)

@@ -294,6 +294,7 @@ int run_model(const pmoc_model* m, long long it0, long long nsteps, int diagnose
   ra.it0 = it0;
   ra.nsteps = nsteps;
   ra.diagnose_only = diagnose_only;
+  ra.sync_refresh = 0;
   const int lpl = lpl_for(m->nz);
   ra.sp = plan_smem(lpl, m->ny, m->nb, ra.m.flags);
   switch (lpl) {
