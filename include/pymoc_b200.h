@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PMOC_ABI_VERSION 2
+#define PMOC_ABI_VERSION 3
 #define PMOC_MAX_NZ_WARP 256 /* one warp per member up to this many levels */
 #define PMOC_MAX_NZ_WIDE 4096 /* one CTA per member up to this many levels ('jn' topology only) */
 #define PMOC_MAX_NY_ML 64    /* SO_ML surface points per member */
@@ -192,8 +192,28 @@ int pmoc_model_run(const pmoc_model* m, int64_t it0, int64_t nsteps, void* strea
  * buffers are allocated, inputs copied in, the fused kernel run, and state + diagnostics
  * copied back before returning (synchronous).  This is the call a non-torch consumer binds. */
 int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nsteps);
-/* bytes the last pmoc_model_run_host of this thread copied host->device / device->host */
+/* bytes the last pmoc_model_run_host / pmoc_host_open / pmoc_host_step of this thread copied
+ * host->device / device->host */
 void pmoc_host_last_bytes(uint64_t* h2d, uint64_t* d2h);
+
+/* Persistent host-buffer handle: the same loop (the examples' `for ii in range(total_iters)` with its
+ * diagnostics every Diag_iters, run_JansenNadeau_2018.py:201-261) for a consumer that keeps its arrays in HOST
+ * memory and calls in every few iterations.  pmoc_host_open mirrors every array of `m` (HOST pointers, which must
+ * stay valid until pmoc_host_close; pin them for full copy bandwidth) on the device once -- grids, parameters,
+ * state -- from a memory pool private to the library, and keeps three streams.  pmoc_host_step advances
+ * iterations [it0, it0 + nsteps) and moves only the array classes asked for, pipelined over blocks of members so
+ * that copies overlap the fused kernel:
+ *   push: copied host->device before the launch (0 = the device copy is current: nothing goes up);
+ *   pull: copied device->host after it.
+ * An order-'post' model is diagnosed first when it0 == 0 (the scripts' pre-loop solve()), or when the state is
+ * pushed without matching streamfunctions before any diagnosis.  Synchronous; returns pmoc_status. */
+#define PMOC_IO_STATE 1u /* b of every column, bs of the mixed layer, bbot / kappa variant of the 'jn' switches, status */
+#define PMOC_IO_PSI 2u   /* the streamfunctions the loop carries: Psi_iso_b/n (Psi_tw without PMOC_ISO), Psi_so, zonal legs */
+#define PMOC_IO_DIAG 4u  /* everything else a diagnosis writes: Psi_tw, psib, bgrid, Psi_Ek, Psi_GM, Psi_s, ... (pull only) */
+typedef struct pmoc_host pmoc_host;
+int pmoc_host_open(const pmoc_model* m, pmoc_host** handle);
+int pmoc_host_step(pmoc_host* handle, int64_t it0, int64_t nsteps, uint32_t push, uint32_t pull);
+int pmoc_host_close(pmoc_host* handle);
 
 /* ---- per-module entry points (the reference's method surface), batched over M ----------- */
 

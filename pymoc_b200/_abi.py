@@ -1,13 +1,14 @@
 """ctypes mirror of ``include/pymoc_b200.h`` (keep the two in sync; ABI version checked at load)."""
 import ctypes as C
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE = range(5)
 STATUS_NAMES = {1: 'EINVAL', 2: 'EUNSUPPORTED', 3: 'ECUDA', 4: 'ENODEVICE'}
 
 HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP, HAS_PAC = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_CONVECT, STAGE_VERTADVDIFF, STAGE_HORADV = 1, 2, 4
+IO_STATE, IO_PSI, IO_DIAG = 1, 2, 4
 ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES, ST_NOISE_SWITCH = 1, 2, 4, 8, 16, 32, 64
 ST_TIE_CELL, ST_BS_SAWTOOTH = 128, 256
 ST_PARITY_UNDEFINED = ST_BS_NONMONOTONE | ST_NOISE_SWITCH | ST_TIE_CELL  # the reference's own result hangs on rounding noise
@@ -60,7 +61,7 @@ class Model(C.Structure):
 
 
 EXPORTS = ('pmoc_abi_version', 'pmoc_last_error', 'pmoc_device_info', 'pmoc_model_scratch_bytes', 'pmoc_model_diagnose', 'pmoc_model_run',
-           'pmoc_model_run_host', 'pmoc_host_last_bytes', 'pmoc_column_timestep', 'pmoc_thermwind_solve', 'pmoc_thermwind_psib',
+           'pmoc_model_run_host', 'pmoc_host_last_bytes', 'pmoc_host_open', 'pmoc_host_step', 'pmoc_host_close', 'pmoc_column_timestep', 'pmoc_thermwind_solve', 'pmoc_thermwind_psib',
            'pmoc_so_solve', 'pmoc_ml_timestep', 'pmoc_fp64_peak')
 
 
@@ -78,6 +79,9 @@ def declare(lib):
   lib.pmoc_model_run_host.argtypes = [P(Model), C.c_int64, C.c_int64]
   lib.pmoc_host_last_bytes.argtypes = [P(C.c_uint64), P(C.c_uint64)]
   lib.pmoc_host_last_bytes.restype = None
+  lib.pmoc_host_open.argtypes = [P(Model), P(C.c_void_p)]
+  lib.pmoc_host_step.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32]
+  lib.pmoc_host_close.argtypes = [C.c_void_p]
   lib.pmoc_column_timestep.argtypes = [C.c_int64, C.c_int32, C.c_void_p, P(Column), Vec, Vec, Vec, C.c_double,
                                        C.c_uint32, C.c_void_p]
   lib.pmoc_thermwind_solve.argtypes = [C.c_int64, C.c_int32, C.c_void_p, Vec, Vec, Vec, Vec, C.c_void_p, C.c_void_p]

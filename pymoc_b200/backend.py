@@ -37,3 +37,45 @@ class CudaBackend:
 
   def sync(self):
     self.torch.cuda.synchronize(self.device)
+
+
+class PinnedHostBackend:
+  """Pinned HOST buffers for the host-pointer entry points of the C ABI (``pmoc_model_run_host``,
+  ``pmoc_host_open/step/close``), which do their own host<->device copies.  Same interface as
+  :class:`CudaBackend`; the buffers are torch tensors in page-locked memory, viewed as numpy arrays."""
+
+  def __init__(self):
+    import torch
+    if not torch.cuda.is_available():
+      raise RuntimeError('pymoc_b200: no CUDA device visible; the engine has no CPU path')
+    from . import _lib
+    self.torch, self.lib, self.bytes_in, self.bytes_out = torch, _lib.lib(), 0, 0
+
+  def upload(self, arr):
+    a = np.ascontiguousarray(arr)
+    t = self.torch.empty(a.shape, dtype=self.torch.from_numpy(a[:0]).dtype, pin_memory=True)
+    t.numpy()[...] = a
+    self.bytes_in += a.nbytes
+    return t
+
+  def zeros(self, shape, dtype=np.float64):
+    tdt = {np.float64: self.torch.float64, np.int32: self.torch.int32, np.uint32: self.torch.int32}[dtype]
+    t = self.torch.zeros(shape, dtype=tdt, pin_memory=True)
+    self.bytes_out += t.numel() * t.element_size()
+    return t
+
+  @staticmethod
+  def ptr(buf):
+    return None if buf is None else buf.data_ptr()
+
+  def download(self, buf):
+    return buf.numpy().copy()
+
+  def assign(self, buf, arr):
+    buf.numpy()[...] = np.asarray(arr).reshape(buf.shape)
+
+  def stream(self):
+    return None
+
+  def sync(self):
+    pass

@@ -1,6 +1,7 @@
 // Host-buffer entry point (pmoc_model_run_host) and the FP64 roofline probe.
 #include "pmoc_common.cuh"
 
+#include <new>
 #include <vector>
 
 static thread_local unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
@@ -28,7 +29,8 @@ struct Mirror {
     size_t slot;       // byte offset of the pointer inside pmoc_model
     size_t per_member; // bytes per member; 0 = shared by all members
     size_t bytes;      // total bytes
-    bool in, out;      // copied in / copied back
+    bool in, out;      // copied in / copied back (pmoc_model_run_host)
+    unsigned cat;      // PMOC_IO_* class of a state / streamfunction / diagnostic array, 0 for parameters (pmoc_host_step)
   };
   cudaStream_t s[kStreams] = {};
   cudaEvent_t shared_ready = nullptr;
@@ -37,10 +39,52 @@ struct Mirror {
   cudaError_t err = cudaSuccess;
   const pmoc_model* h;
   pmoc_model d;
+  cudaMemPool_t pool = nullptr;
+  unsigned cat = 0;  // class given to the fields registered next
+
+  // Streams, event and the library's own memory pool.  The pool is private (one per device, created on first
+  // use, kept for the life of the process with its memory retained between calls): the embedding application's
+  // default pool is not touched.
+  cudaError_t init() {
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (!pools[dev]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if ((e = cudaMemPoolCreate(&pools[dev], &props)) != cudaSuccess) return e;
+      unsigned long long keep = ~0ull;
+      if ((e = cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep)) != cudaSuccess) return e;
+    }
+    pool = pools[dev];
+    for (int i = 0; i < kStreams; ++i)
+      if ((e = cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+    return cudaEventCreateWithFlags(&shared_ready, cudaEventDisableTiming);
+  }
+  // frees what init() and alloc() acquired, on every path (streams and event may be partly created)
+  cudaError_t fini() {
+    cudaError_t e = cudaSuccess;
+    for (int i = kStreams - 1; i >= 0; --i) {  // stream 0 last: it owns the allocations
+      if (i == 0) release();
+      if (s[i]) {
+        const cudaError_t ei = cudaStreamSynchronize(s[i]);
+        if (e == cudaSuccess) e = ei;
+      }
+    }
+    for (int i = 0; i < kStreams; ++i)
+      if (s[i]) { cudaStreamDestroy(s[i]); s[i] = nullptr; }
+    if (shared_ready) { cudaEventDestroy(shared_ready); shared_ready = nullptr; }
+    return e;
+  }
 
   void* alloc(size_t bytes) {
     void* p = nullptr;
-    if (err == cudaSuccess) err = cudaMallocAsync(&p, bytes ? bytes : 8, s[0]);
+    if (err == cudaSuccess) err = cudaMallocFromPoolAsync(&p, bytes ? bytes : 8, pool, s[0]);
     if (p) allocs.push_back(p);
     return p;
   }
@@ -49,7 +93,7 @@ struct Mirror {
   void add(P* slot, const void* hp, size_t per_member, size_t bytes, bool in, bool out) {
     if (!hp) return;
     char* dp = static_cast<char*>(alloc(bytes));
-    fields.push_back({(char*)hp, dp, (size_t)((char*)slot - (char*)&d), per_member, bytes, in, out});
+    fields.push_back({(char*)hp, dp, (size_t)((char*)slot - (char*)&d), per_member, bytes, in, out, cat});
     *slot = reinterpret_cast<P>(dp);
   }
   void vec(pmoc_vec* dv, long long M, size_t len) {  // input vector: per member when mstride != 0
@@ -65,15 +109,17 @@ struct Mirror {
     add(dp, *dp, len * sizeof(T), (size_t)M * len * sizeof(T), upload, download);
   }
   void column(pmoc_column* c, long long M, int nz) {
+    cat = PMOC_IO_STATE;
     state(&c->b, M, nz, true);
+    state(&c->bbot, M, 1, true);
+    state(&c->var, M, 1, true);
+    cat = 0;
     vec(&c->kappa, M, (size_t)c->nvar * nz);
     vec(&c->dAk, M, (size_t)c->nvar * nz);
     vec(&c->Area, M, nz);
     vec(&c->bs, M, 1);
     vec(&c->N2min, M, 1);
     vec(&c->bzbot, M, 1);
-    state(&c->bbot, M, 1, true);
-    state(&c->var, M, 1, true);
   }
   void upload_shared() {
     for (auto& f : fields)
@@ -93,6 +139,23 @@ struct Mirror {
       err = f.in ? cudaMemcpyAsync(f.dev + off, f.host + off, len, cudaMemcpyHostToDevice, st)
                  : cudaMemsetAsync(f.dev + off, 0, len, st);
       if (f.in) g_h2d_bytes += len;
+    }
+  }
+  // pmoc_host_step: only the per-member arrays whose class is in `mask` move
+  void push_block(long long m0, long long n, unsigned mask, cudaStream_t st) {
+    for (auto& f : fields) {
+      if (!f.per_member || !(f.cat & mask) || err != cudaSuccess) continue;
+      const size_t off = (size_t)m0 * f.per_member;
+      err = cudaMemcpyAsync(f.dev + off, f.host + off, (size_t)n * f.per_member, cudaMemcpyHostToDevice, st);
+      g_h2d_bytes += (size_t)n * f.per_member;
+    }
+  }
+  void pull_block(long long m0, long long n, unsigned mask, cudaStream_t st) {
+    for (auto& f : fields) {
+      if (!f.per_member || !(f.cat & mask) || err != cudaSuccess) continue;
+      const size_t off = (size_t)m0 * f.per_member;
+      err = cudaMemcpyAsync(f.host + off, f.dev + off, (size_t)n * f.per_member, cudaMemcpyDeviceToHost, st);
+      g_d2h_bytes += (size_t)n * f.per_member;
     }
   }
   void download_block(long long m0, long long n, cudaStream_t st) {
@@ -115,6 +178,88 @@ struct Mirror {
     for (void* p : allocs) cudaFreeAsync(p, s[0]);
     allocs.clear();
   }
+
+  // Register every array of the model.  `carry` / `rewritten` say which streamfunctions one stateless call
+  // uploads / brings back (pmoc_model_run_host); the handle API moves them by class instead.
+  void describe(bool carry, bool rewritten, bool stepped) {
+    const long long M = d.M;
+    const int nz = d.nz, ny = d.ny, nb = d.nb;
+    const unsigned f = d.flags;
+    cat = 0;
+    shared(&d.z, nz);
+    shared(&d.y, ny);
+    column(&d.basin, M, nz);
+    if (f & PMOC_HAS_NORTH) column(&d.north, M, nz);
+    if (f & PMOC_HAS_PAC) {
+      column(&d.pac, M, nz);
+      vec(&d.zoc_f, M, 1);
+      vec(&d.so2_L, M, 1);
+      cat = PMOC_IO_DIAG; state(&d.Psi_zoc, M, nz, false, rewritten);
+      cat = PMOC_IO_PSI; state(&d.Psi_zon_a, M, nz, carry, rewritten);
+      state(&d.Psi_zon_p, M, nz, carry, rewritten);
+      cat = PMOC_IO_DIAG; state(&d.psib2, M, nb, false, rewritten);
+      state(&d.bgrid2, M, nb, false, rewritten);
+      cat = PMOC_IO_PSI; state(&d.Psi_so2, M, nz, carry, rewritten);
+      cat = PMOC_IO_DIAG; state(&d.Psi_Ek2, M, nz, false, rewritten);
+      state(&d.Psi_GM2, M, nz, false, rewritten);
+      cat = 0;
+    }
+    vec(&d.tw_f, M, 1);
+    vec(&d.tw_b2, M, nz);
+    vec(&d.so_bs, M, ny);
+    vec(&d.so_tau, M, d.so_tau_on_y ? ny : 1);
+    vec(&d.so_f, M, 1);
+    vec(&d.so_rho, M, 1);
+    vec(&d.so_L, M, 1);
+    vec(&d.so_KGM, M, 1);
+    vec(&d.so_smax, M, 1);
+    vec(&d.so_c, M, 1);
+    shared(&d.so_sill_taper, nz);
+    shared(&d.so_ek_taper, nz);
+    shared(&d.so_top_taper, nz);
+    shared(&d.so_bot_taper, nz);
+    cat = PMOC_IO_STATE; state(&d.ml_bs, M, ny, true);
+    cat = 0;
+    vec(&d.ml_Ks, M, 1);
+    vec(&d.ml_h, M, 1);
+    vec(&d.ml_L, M, 1);
+    vec(&d.ml_vpist, M, 1);
+    vec(&d.ml_surflux, M, ny);
+    vec(&d.ml_rest_mask, M, ny);
+    vec(&d.ml_b_rest, M, ny);
+    const bool iso = (f & PMOC_ISO) != 0;
+    cat = iso ? PMOC_IO_DIAG : PMOC_IO_PSI; state(&d.Psi_tw, M, nz, carry && !iso, rewritten);
+    cat = PMOC_IO_PSI; state(&d.Psi_iso_b, M, nz, carry, rewritten);
+    state(&d.Psi_iso_n, M, nz, carry, rewritten);
+    cat = PMOC_IO_DIAG; state(&d.psib, M, nb, false, rewritten);
+    state(&d.bgrid, M, nb, false, rewritten);
+    cat = PMOC_IO_PSI; state(&d.Psi_so, M, nz, carry, rewritten);
+    cat = PMOC_IO_DIAG; state(&d.Psi_Ek, M, nz, false, rewritten);
+    state(&d.Psi_GM, M, nz, false, rewritten);
+    state(&d.ml_Psi_s, M, ny, false, stepped);
+    cat = PMOC_IO_STATE; state(&d.status, M, 1, true);
+    cat = 0;
+  }
+  // blocks of members: enough of them to overlap copies with kernels, each large enough to fill the GPU; one
+  // scratch buffer per stream for the block-per-member kernels (nz > 256)
+  long long nblk = 1, per = 0;
+  void* scratch[kStreams] = {};
+  void plan_blocks() {
+    const long long M = d.M;
+    nblk = M / PMOC_HOST_BLOCK_MEMBERS;
+    if (nblk < 1) nblk = 1;
+    if (nblk > 32) nblk = 32;
+    per = (M + nblk - 1) / nblk;
+    d.scratch = nullptr;
+    d.scratch_bytes = 0;
+    pmoc_model one = *h;
+    one.M = per;
+    const uint64_t need = pmoc_model_scratch_bytes(&one);
+    if (need) {
+      for (int i = 0; i < kStreams && i < nblk; ++i) scratch[i] = alloc((size_t)need);
+      d.scratch_bytes = need;
+    }
+  }
 };
 
 }  // namespace
@@ -130,124 +275,148 @@ extern "C" int pmoc_model_run_host(const pmoc_model* m, int64_t it0, int64_t nst
 #else
   if (m->M <= 0 || m->nz < 3) return fail(PMOC_EINVAL, "bad M / nz");
   const long long M = m->M;
-  const int nz = m->nz, ny = m->ny, nb = m->nb;
   const unsigned f = m->flags;
   Mirror mr;
-  {  // keep the stream-ordered pool's memory between calls (the default trims it at every synchronisation)
-    int dev = 0;
-    cudaMemPool_t pool;
-    unsigned long long keep = ~0ull;
-    PM_CUDA_OK(cudaGetDevice(&dev));
-    PM_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
-    PM_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
-  for (int i = 0; i < kStreams; ++i) PM_CUDA_OK(cudaStreamCreateWithFlags(&mr.s[i], cudaStreamNonBlocking));
-  PM_CUDA_OK(cudaEventCreateWithFlags(&mr.shared_ready, cudaEventDisableTiming));
   mr.h = m;
   mr.d = *m;
-  pmoc_model& d = mr.d;
-  // Diagnostics: the kernel rewrites all of them at the last iteration with ii % K == 0 of the launch (and the
-  // pre-loop diagnosis of an order-'post' model at it0 == 0 does); without such an iteration they are left
-  // alone on both sides.  Only the streamfunctions the step loop carries from an earlier launch are inputs.
-  const long long K = m->K > 0 ? m->K : 1;
-  const bool jn = (f & PMOC_ORDER_JN) != 0;
-  const bool rewritten = (!jn && it0 == 0) || (nsteps > 0 && ((it0 + nsteps - 1) / K) * K >= it0);
-  const bool carry = jn ? (it0 % K != 0) : (it0 > 0);
-  mr.shared(&d.z, nz);
-  mr.shared(&d.y, ny);
-  mr.column(&d.basin, M, nz);
-  if (f & PMOC_HAS_NORTH) mr.column(&d.north, M, nz);
-  if (f & PMOC_HAS_PAC) {
-    mr.column(&d.pac, M, nz);
-    mr.vec(&d.zoc_f, M, 1);
-    mr.vec(&d.so2_L, M, 1);
-    mr.state(&d.Psi_zoc, M, nz, false, rewritten);
-    mr.state(&d.Psi_zon_a, M, nz, carry, rewritten);
-    mr.state(&d.Psi_zon_p, M, nz, carry, rewritten);
-    mr.state(&d.psib2, M, nb, false, rewritten);
-    mr.state(&d.bgrid2, M, nb, false, rewritten);
-    mr.state(&d.Psi_so2, M, nz, carry, rewritten);
-    mr.state(&d.Psi_Ek2, M, nz, false, rewritten);
-    mr.state(&d.Psi_GM2, M, nz, false, rewritten);
-  }
-  mr.vec(&d.tw_f, M, 1);
-  mr.vec(&d.tw_b2, M, nz);
-  mr.vec(&d.so_bs, M, ny);
-  mr.vec(&d.so_tau, M, m->so_tau_on_y ? ny : 1);
-  mr.vec(&d.so_f, M, 1);
-  mr.vec(&d.so_rho, M, 1);
-  mr.vec(&d.so_L, M, 1);
-  mr.vec(&d.so_KGM, M, 1);
-  mr.vec(&d.so_smax, M, 1);
-  mr.vec(&d.so_c, M, 1);
-  mr.shared(&d.so_sill_taper, nz);
-  mr.shared(&d.so_ek_taper, nz);
-  mr.shared(&d.so_top_taper, nz);
-  mr.shared(&d.so_bot_taper, nz);
-  mr.state(&d.ml_bs, M, ny, true);
-  mr.vec(&d.ml_Ks, M, 1);
-  mr.vec(&d.ml_h, M, 1);
-  mr.vec(&d.ml_L, M, 1);
-  mr.vec(&d.ml_vpist, M, 1);
-  mr.vec(&d.ml_surflux, M, ny);
-  mr.vec(&d.ml_rest_mask, M, ny);
-  mr.vec(&d.ml_b_rest, M, ny);
-  mr.state(&d.Psi_tw, M, nz, carry && !(f & PMOC_ISO), rewritten);
-  mr.state(&d.Psi_iso_b, M, nz, carry, rewritten);
-  mr.state(&d.Psi_iso_n, M, nz, carry, rewritten);
-  mr.state(&d.psib, M, nb, false, rewritten);
-  mr.state(&d.bgrid, M, nb, false, rewritten);
-  mr.state(&d.Psi_so, M, nz, carry, rewritten);
-  mr.state(&d.Psi_Ek, M, nz, false, rewritten);
-  mr.state(&d.Psi_GM, M, nz, false, rewritten);
-  mr.state(&d.ml_Psi_s, M, ny, false, nsteps > 0);
-  mr.state(&d.status, M, 1, true);
-  // blocks of members: enough of them to overlap copies with kernels, each large enough to fill the GPU
-  long long nblk = M / PMOC_HOST_BLOCK_MEMBERS;
-  if (nblk < 1) nblk = 1;
-  if (nblk > 32) nblk = 32;
-  const long long per = (M + nblk - 1) / nblk;
-  void* scratch[kStreams] = {};
-  d.scratch = nullptr;
-  d.scratch_bytes = 0;
-  {  // block-per-member kernels (nz > 256): one scratch buffer per stream, sized for a block
-    pmoc_model one = *m;
-    one.M = per;
-    const uint64_t need = pmoc_model_scratch_bytes(&one);
-    if (need) {
-      for (int i = 0; i < kStreams && i < nblk; ++i) scratch[i] = mr.alloc((size_t)need);
-      d.scratch_bytes = need;
-    }
-  }
   int rc = PMOC_OK;
+  mr.err = mr.init();
+  if (mr.err == cudaSuccess) {
+    // Diagnostics: the kernel rewrites all of them at the last iteration with ii % K == 0 of the launch (and the
+    // pre-loop diagnosis of an order-'post' model at it0 == 0 does); without such an iteration they are left
+    // alone on both sides.  Only the streamfunctions the step loop carries from an earlier launch are inputs.
+    const long long K = m->K > 0 ? m->K : 1;
+    const bool jn = (f & PMOC_ORDER_JN) != 0;
+    const bool rewritten = (!jn && it0 == 0) || (nsteps > 0 && ((it0 + nsteps - 1) / K) * K >= it0);
+    const bool carry = jn ? (it0 % K != 0) : (it0 > 0);
+    mr.describe(carry, rewritten, nsteps > 0);
+    mr.plan_blocks();
+  }
   if (mr.err == cudaSuccess) {
     mr.upload_shared();
     for (int i = 1; i < kStreams && mr.err == cudaSuccess; ++i) mr.err = cudaStreamWaitEvent(mr.s[i], mr.shared_ready, 0);
-    for (long long c = 0; c < nblk && rc == PMOC_OK && mr.err == cudaSuccess; ++c) {
-      const long long m0 = c * per, n = (m0 + per <= M ? per : M - m0);
+    for (long long c = 0; c < mr.nblk && rc == PMOC_OK && mr.err == cudaSuccess; ++c) {
+      const long long m0 = c * mr.per, n = (m0 + mr.per <= M ? mr.per : M - m0);
       if (n <= 0) break;
       cudaStream_t st = mr.s[c % kStreams];
       mr.upload_block(m0, n, M, st);
       pmoc_model blk = mr.block_model(m0, n);
-      blk.scratch = scratch[c % kStreams];
+      blk.scratch = mr.scratch[c % kStreams];
       if (it0 == 0 && !(f & PMOC_ORDER_JN)) rc = pmoc_model_diagnose(&blk, st);
       if (rc == PMOC_OK) rc = pmoc_model_run(&blk, it0, nsteps, st);
       if (rc == PMOC_OK) mr.download_block(m0, n, st);
     }
   }
-  cudaError_t e = cudaSuccess;
-  for (int i = kStreams - 1; i >= 0; --i) {  // stream 0 last: it owns the allocations
-    if (i == 0) mr.release();
-    const cudaError_t ei = cudaStreamSynchronize(mr.s[i]);
-    if (e == cudaSuccess) e = ei;
-  }
-  for (int i = 0; i < kStreams; ++i) cudaStreamDestroy(mr.s[i]);
-  cudaEventDestroy(mr.shared_ready);
+  const cudaError_t e = mr.fini();  // every path: streams, event and device memory are returned
   if (rc != PMOC_OK) return rc;
   PM_CUDA_OK(mr.err);
   PM_CUDA_OK(e);
   return PMOC_OK;
 #endif
+}
+
+// ---- persistent handle: parameters uploaded once, streams and device mirrors kept between calls ------------
+struct pmoc_host {
+#ifndef PMOC_EMU
+  Mirror mr;
+#endif
+  pmoc_model host;  // the caller's struct (host pointers), copied
+  bool diagnosed = false;
+};
+
+extern "C" int pmoc_host_open(const pmoc_model* m, pmoc_host** out) {
+  if (!m || !out) return fail(PMOC_EINVAL, "model / handle pointer is NULL");
+  *out = nullptr;
+  if (m->M <= 0 || m->nz < 3) return fail(PMOC_EINVAL, "bad M / nz");
+  pmoc_host* h = new (std::nothrow) pmoc_host();
+  if (!h) return fail(PMOC_EINVAL, "out of host memory");
+  h->host = *m;
+  g_h2d_bytes = g_d2h_bytes = 0;
+#ifndef PMOC_EMU
+  Mirror& mr = h->mr;
+  mr.h = &h->host;
+  mr.d = *m;
+  mr.err = mr.init();
+  if (mr.err == cudaSuccess) {
+    mr.describe(true, true, true);
+    mr.plan_blocks();
+  }
+  if (mr.err == cudaSuccess) {  // everything goes up once: grids, parameters, state, carried streamfunctions
+    mr.upload_shared();
+    for (auto& f : mr.fields) {
+      if (!f.per_member || mr.err != cudaSuccess) continue;
+      if (f.cat == PMOC_IO_DIAG) {  // outputs
+        mr.err = cudaMemsetAsync(f.dev, 0, f.bytes, mr.s[0]);
+        continue;
+      }
+      mr.err = cudaMemcpyAsync(f.dev, f.host, f.bytes, cudaMemcpyHostToDevice, mr.s[0]);
+      g_h2d_bytes += f.bytes;
+    }
+    if (mr.err == cudaSuccess) mr.err = cudaStreamSynchronize(mr.s[0]);
+  }
+  if (mr.err != cudaSuccess) {
+    const cudaError_t keep = mr.err;
+    mr.fini();
+    delete h;
+    PM_CUDA_OK(keep);
+  }
+#endif
+  *out = h;
+  return PMOC_OK;
+}
+
+extern "C" int pmoc_host_step(pmoc_host* h, int64_t it0, int64_t nsteps, uint32_t push, uint32_t pull) {
+  if (!h) return fail(PMOC_EINVAL, "handle is NULL");
+  if ((push | pull) & ~(PMOC_IO_STATE | PMOC_IO_PSI | PMOC_IO_DIAG)) return fail(PMOC_EINVAL, "unknown PMOC_IO_* bit");
+  if (push & PMOC_IO_DIAG) return fail(PMOC_EINVAL, "diagnostics are outputs: they cannot be pushed");
+  g_h2d_bytes = g_d2h_bytes = 0;
+  const bool jn = (h->host.flags & PMOC_ORDER_JN) != 0;
+  // an order-'post' loop is entered with diagnosed streamfunctions (the scripts' pre-loop solve()): at it0 == 0,
+  // and whenever the caller replaces the state without supplying streamfunctions that match it
+  const bool need_diag = !jn && (it0 == 0 || ((push & PMOC_IO_STATE) && !(push & PMOC_IO_PSI) && !h->diagnosed));
+#ifdef PMOC_EMU
+  if (need_diag)
+    if (int rc = pmoc_model_diagnose(&h->host, nullptr)) return rc;
+  h->diagnosed = true;
+  return pmoc_model_run(&h->host, it0, nsteps, nullptr);
+#else
+  Mirror& mr = h->mr;
+  const long long M = mr.d.M;
+  int rc = PMOC_OK;
+  for (long long c = 0; c < mr.nblk && rc == PMOC_OK && mr.err == cudaSuccess; ++c) {
+    const long long m0 = c * mr.per, n = (m0 + mr.per <= M ? mr.per : M - m0);
+    if (n <= 0) break;
+    cudaStream_t st = mr.s[c % kStreams];
+    if (push) mr.push_block(m0, n, push, st);
+    pmoc_model blk = mr.block_model(m0, n);
+    blk.scratch = mr.scratch[c % kStreams];
+    if (need_diag) rc = pmoc_model_diagnose(&blk, st);
+    if (rc == PMOC_OK && nsteps > 0) rc = pmoc_model_run(&blk, it0, nsteps, st);
+    if (rc == PMOC_OK && pull) mr.pull_block(m0, n, pull, st);
+  }
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < kStreams; ++i) {
+    const cudaError_t ei = cudaStreamSynchronize(mr.s[i]);
+    if (e == cudaSuccess) e = ei;
+  }
+  if (rc != PMOC_OK) return rc;
+  PM_CUDA_OK(mr.err);
+  PM_CUDA_OK(e);
+  h->diagnosed = true;
+  return PMOC_OK;
+#endif
+}
+
+extern "C" int pmoc_host_close(pmoc_host* h) {
+  if (!h) return PMOC_OK;
+#ifndef PMOC_EMU
+  const cudaError_t e = h->mr.fini();
+  delete h;
+  PM_CUDA_OK(e);
+#else
+  delete h;
+#endif
+  return PMOC_OK;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -248,3 +248,53 @@ class Ensemble:
   def buffer(self, name):
     """The live device buffer behind a state/diagnostic array (for gathers and checkpoints)."""
     return self._bufs[name]
+
+
+class HostEnsemble(Ensemble):
+  """An ensemble whose arrays live in pinned HOST memory, stepped through the persistent host-buffer handle of
+  the C ABI (``pmoc_host_open / pmoc_host_step / pmoc_host_close``): grids and parameters go to the GPU once,
+  each :meth:`run` moves only the array classes asked for (``push`` before the launch, ``pull`` after it),
+  pipelined over blocks of members.  This is the call pattern of a script that keeps the model state on the
+  host and looks at diagnostics every ``Diag_iters`` iterations (examples/run_JansenNadeau_2018.py:218-226).
+
+      ens = HostEnsemble(spec)
+      for _ in range(total_iters // 120):
+        ens.run(120, pull=IO_STATE | IO_PSI)      # state() / diagnostics() then read the host arrays
+  """
+  IO_STATE, IO_PSI, IO_DIAG = _abi.IO_STATE, _abi.IO_PSI, _abi.IO_DIAG
+
+  def __init__(self, spec: ModelSpec, backend=None, members=None):
+    if backend is None:
+      from .backend import PinnedHostBackend
+      backend = PinnedHostBackend()
+    super().__init__(spec, backend=backend, members=members)
+    self._handle = ctypes.c_void_p()
+    _abi.check(self.lib, self.lib.pmoc_host_open(ctypes.byref(self.model), ctypes.byref(self._handle)))
+
+  def run(self, nsteps, push=0, pull=_abi.IO_STATE | _abi.IO_PSI | _abi.IO_DIAG, sync=True):
+    """Advance ``nsteps`` iterations.  ``push``: classes of host arrays copied to the device first (after the
+    caller changed them: ``IO_STATE`` for a new state); ``pull``: classes copied back."""
+    if self._handle is None:
+      raise RuntimeError('HostEnsemble is closed')
+    _abi.check(self.lib, self.lib.pmoc_host_step(self._handle, self.it, int(nsteps), int(push), int(pull)))
+    self.it += int(nsteps)
+
+  def diagnose(self):
+    _abi.check(self.lib, self.lib.pmoc_host_step(self._handle, 0, 0, 0, _abi.IO_PSI | _abi.IO_DIAG))
+
+  def last_bytes(self):
+    """(host->device, device->host) bytes of the last call."""
+    h2d, d2h = ctypes.c_uint64(), ctypes.c_uint64()
+    self.lib.pmoc_host_last_bytes(ctypes.byref(h2d), ctypes.byref(d2h))
+    return int(h2d.value), int(d2h.value)
+
+  def close(self):
+    if getattr(self, '_handle', None) is not None and self._handle:
+      self.lib.pmoc_host_close(self._handle)
+    self._handle = None
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass

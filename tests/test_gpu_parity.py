@@ -199,3 +199,34 @@ def test_c4_lattice_long_run(cuda):
 def test_f2010_smoother_is_the_converged_solution(cuda):
   from parity_common import f2010_smoother_converged
   print('F2010 smoother vs solve_bvp(tol=1e-8): worst %.2e' % f2010_smoother_converged(cuda, bvp_tol=1e-8, tol=1e-8))
+
+
+def test_host_handle_matches_device_path(cuda):
+  """pmoc_host_open / pmoc_host_step / pmoc_host_close (persistent host-buffer handle: parameters uploaded once,
+  per call only the requested array classes move) == the device path, bit for bit -- with nothing pulled between
+  calls, with state + streamfunctions pulled and pushed back every call, and across a diagnosis boundary."""
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble, HostEnsemble
+  S, P, D = HostEnsemble.IO_STATE, HostEnsemble.IO_PSI, HostEnsemble.IO_DIAG
+  for spec, keys in ((configs.c3_twocol_so(16, axes=(2, 2, 2, 2)), ('Psi_tw', 'Psi_iso_b', 'Psi_so', 'psib')),
+                     (configs.c2_column_so(32768), ('Psi_so', 'Psi_Ek', 'Psi_GM')),
+                     (configs.c4_jansen_nadeau(16384), ('Psi_iso_b', 'Psi_so', 'Psi_s', 'bbot_basin')),
+                     (configs.c5_single_global_basin(8192, nz=320, dt_days=1., kapfac_max=1.), ('Psi_iso_b', 'Psi_so'))):
+    dev = Ensemble(spec, backend=cuda)
+    dev.run(30)
+    a = HostEnsemble(spec)
+    a.run(13, pull=0)
+    assert a.last_bytes() == (0, 0)  # nothing moved: parameters and state are resident
+    a.run(17, pull=S | P | D)
+    b = HostEnsemble(spec)
+    b.run(13, pull=S | P)
+    b.run(17, push=S | P, pull=S | P | D)  # the host copy is the truth: up, 17 steps, down
+    h2d, d2h = b.last_bytes()
+    assert h2d > 0 and d2h > h2d
+    for ens in (a, b):
+      for key, val in dev.state().items():
+        assert np.array_equal(val, ens.state()[key], equal_nan=True), (spec.name, key)
+      for key in keys:
+        assert np.array_equal(dev.diagnostics()[key], ens.diagnostics()[key], equal_nan=True), (spec.name, key)
+      assert np.array_equal(dev.diagnostics()['status'], ens.diagnostics()['status'])
+      ens.close()
