@@ -5,7 +5,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libpymoc_b200.so')
+LIB_PATH = os.environ.get('PMOC_B200_LIB') or os.path.join(_HERE, 'libpymoc_b200.so')  # (the override is for tuning builds)
 _lib = None
 
 

@@ -47,6 +47,17 @@ def _compile(src, obj, defs):
   return obj
 
 
+def build_variant(out, extra_flags, only_lpl=None):
+  """Tuning builds: the same sources with extra nvcc flags into another library (loaded with PMOC_B200_LIB=<path>)."""
+  global OBJ, LIB, NVCC_FLAGS, LPLS
+  saved = OBJ, LIB, NVCC_FLAGS, LPLS
+  OBJ, LIB, NVCC_FLAGS = OBJ + '_' + os.path.basename(out), out, NVCC_FLAGS + list(extra_flags)
+  try:
+    return build(force=False, verbose=True)
+  finally:
+    OBJ, LIB, NVCC_FLAGS, LPLS = saved
+
+
 def build(force=False, verbose=True):
   os.makedirs(OBJ, exist_ok=True)
   stamp = os.path.join(OBJ, 'stamp')
@@ -68,4 +79,8 @@ def build(force=False, verbose=True):
 
 
 if __name__ == '__main__':
-  build(force='--force' in sys.argv)
+  if '--variant' in sys.argv:  # python -m pymoc_b200.build --variant <out.so> <nvcc flag> ...
+    i = sys.argv.index('--variant')
+    build_variant(sys.argv[i + 1], sys.argv[i + 2:])
+  else:
+    build(force='--force' in sys.argv)

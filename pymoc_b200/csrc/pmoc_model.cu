@@ -324,6 +324,9 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
   const long long last_refresh = ((it_end - 1) / K) * K;
   const bool two_var_b = M.basin.nvar > 1, two_var_n = M.north.nvar > 1;
   long long ii = a.it0;
+  // next iteration with it % K == 0 at or after ii: kept incrementally (a 64-bit integer division costs ~100
+  // instructions, which at K = 1 was 6 % of the C1 kernel)
+  long long next0 = ((ii + K - 1) / K) * K;
   bool refresh_next = dg || (ML && ii < it_end && ii % K == 0);
   bool wr = dg || ii == last_refresh;
   for (;;) {
@@ -337,9 +340,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
     }
     if (ii >= it_end) break;
     if (!ML) {
-      const long long stop = ((ii + K - 1) / K) * K;  // next iteration with it % K == 0
+      const long long stop = next0;  // next iteration with it % K == 0
       const bool hits = stop < it_end;
       const int n = (int)((hits ? stop + 1 : it_end) - ii);
+      if (hits) next0 = stop + K;
       for (int s = 0; s < n; ++s) {
         col_advance<LPL>(cb, G, nz);
         if (NORTH) col_advance<LPL>(cn, G, nz);
@@ -349,7 +353,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(32 * max_warps(TOPO), 1) k_model(RunArgs a) {
       refresh_next = hits;
       wr = stop == last_refresh;
     } else {
-      long long stop = (ii / K + 1) * K;
+      if (next0 <= ii) next0 += K;  // here ii % K == 0 was just diagnosed (or the launch starts inside an interval)
+      long long stop = next0;
       if (stop > it_end) stop = it_end;
       for (; ii < stop; ++ii) {
         // bottom boundary condition and bottom-boundary-layer kappa (:233-254); levels 0 and 1

@@ -10,6 +10,7 @@
 // (k_wide_refresh) and the host loop in pmoc_run_model_wide alternates the two.
 #include "pmoc_common.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace pmk {
@@ -21,6 +22,7 @@ struct WideArgs {
   long long it0, nsteps;
   double* geo;   // scratch: [4][nz] dzu, 1/dzu, dzc, 1/dzc (shared by all members)
   double* memb;  // scratch: per member [6][nz]: -weff basin v0, v1, -weff north v0, v1, 1/Area basin, 1/Area north
+  int force_late;  // test hook (PMOC_WIDE_FORCE_LATE=1): always take the serial schedule of the basin column
 };
 
 PM_DEV int wtid() { return rt::warp_in_block() * 32 + rt::lane(); }
@@ -368,18 +370,37 @@ PM_GLOBAL void k_wide_refresh(WideArgs a) {
 // scratch buffer by their owner when a boundary switch flips the variant).  What the neighbours and
 // the mixed layer need is published once per step: the basin profile in natural order with one pad
 // word per LPT levels (conflict-free stores, read through pm::PadIdx) and the first/last northern
-// level of every thread.  The last warp also runs SO_ML, whose state is parked in shared memory
-// between its steps (the register file is full of column state: 8 warps x 255 registers); three
-// block barriers per step.  The arithmetic is the bit-faithful step of pm::col_step_exact.
+// level of every thread.  The arithmetic is the bit-faithful step of pm::col_step_exact.
+//
+// SO_ML runs on a ninth warp of its own, one step behind the columns.  The script's order is
+// columns(ii) -> SO_ML(ii) -> columns(ii+1), but columns(ii+1) sees SO_ML(ii) only through
+// channel.bs[0] in the bottom-boundary switches of the basin (run_JansenNadeau_2018.py:235-246): its
+// bottom value bbot, i.e. levels 0 and 1 of thread 0, and -- only when Psi_SO[1] >= 0, Psi_res_b[1] > 0
+// and north.b[0] < basin.b[1] -- the choice of the kappa profile.  So per iteration:
+//   phase 1   the mixed-layer warp does SO_ML(ii-1) on the profile published after columns(ii-1) (a single
+//             dependent chain of ~900 instructions) WHILE the column warps do columns(ii): the whole northern
+//             column, and the basin except the two bottom levels (thread 0 keeps the gradient of cell 1-2);
+//   barrier;
+//   phase 2   bs[0] is known: the switches are evaluated exactly as written, thread 0 finishes basin levels
+//             0 and 1, everything is published;  barrier.
+// In the rare "late" case (the kappa choice hangs on bs[0]) the basin column waits for phase 2.  Same
+// operations on the same operands as the serial order: bit-identical results; the SO_ML chain, which
+// was 60 % of the step with seven warps idle at a barrier, is hidden behind the column work.
+//
+// PIPE = false (16 levels per thread, nz > 2048): a ninth warp would put three warps on one SM sub-partition
+// and cap the kernel at 168 registers, and with 80 doubles of column state per thread the spills then cost more
+// than the overlap gains (measured at nz = 4096: 65 ms against 52 ms).  There the eighth column warp runs SO_ML
+// after its own column work, its state parked in shared memory: same schedule and barriers, no overlap.
+// Measured gain of the pipelined form: nz = 1024 +18 %, nz = 2048 +10 %.
 constexpr int kWideCol = 256;
-constexpr int kWideAll = kWideCol;
 
-template <int LPT, int SH>
-PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
+template <int LPT, int SH, bool PIPE>
+PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideCol + (PIPE ? 32 : 0), 1) k_wide_steps2(WideArgs a) {
+  constexpr int kWideAll = kWideCol + (PIPE ? 32 : 0);
   static_assert((1 << SH) == LPT && LPT >= 2, "LPT = 2^SH >= 2");
   const pmoc_model& M = a.m;
   const int nz = M.nz, ny = M.ny, t = wtid(), W = rt::warp_in_block(), Ln = rt::lane();
-  const bool col = t < kWideCol, mlw = W == kWideCol / 32 - 1;
+  const bool col = t < kWideCol, mlw = W == (PIPE ? kWideCol / 32 : kWideCol / 32 - 1);
   const long long m = rt::block_idx();
   const double dt = M.dt;
   constexpr int nzp = kWideCol * LPT;
@@ -395,7 +416,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
   double* dbox = ysm + nyp;                           // [0] = bs[0] of the mixed layer
   int* ibox = reinterpret_cast<int*>(dbox + 8);       // 2 x 8 step flags, then 4 ints for the block collectives
   int* cbox = ibox + 16;
-  double* mlp = dbox + 8 + 10;                        // parked mixed layer, pm::kMlSave
+  double* mlp = dbox + 8 + 10;                        // parked mixed layer (PIPE = false), pm::kMlSave
   const pm::PadIdx bbx{bbp, SH};
   const double* z = M.z;
   const int lo = t * LPT;
@@ -427,7 +448,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
     const int i = lo + j;
     bb[j] = bn[j] = 0.;
     dzu[j] = rdzu[j] = rdzc[j] = 1.;
-    {  // boundary and padding levels: zero -weff and kappa make their update an exact no-op
+    if (col) {  // boundary and padding levels: zero -weff and kappa make their update an exact no-op
       const int s = j * kWideCol + t;
       nwb[s] = nwn[s] = kb[s] = kn[s] = 0.0;
     }
@@ -472,8 +493,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
   rt::syncblock();
   for (int i = t; i < nz && i < fnz; i += kWideAll) pm_s[i] = held;
 
+  pm::MlState ml{};  // PIPE: lives in the registers of the mixed-layer warp; otherwise parked in shared memory
   if (mlw) {
-    pm::MlState ml{};
     pm::ml_setup(ml, ysm, ny, vat(M.ml_Ks, m), vat(M.ml_h, m), vat(M.ml_L, m), vat(M.ml_vpist, m), vrow(M.ml_surflux, m),
                  vrow(M.ml_rest_mask, m), vrow(M.ml_b_rest, m), dt, scan_s);
     ml.first_pos = fpos == 0x7fffffff ? -1 : fpos;
@@ -483,7 +504,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
       dbox[0] = ml.bs[0];
       for (int k = 0; k < 16; ++k) ibox[k] = (k & 7) == 2 || (k & 7) == 3 ? -1 : 0;
     }
-    pm::ml_park(ml, mlp, true);
+    if (!PIPE) pm::ml_park(ml, mlp, true);
   }
   rt::syncblock();
 
@@ -530,36 +551,65 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
     else
       publish_as(q, std::false_type{});
   };
-  publish(0);
+  if (col) publish(0);
   rt::syncblock();
 
   int p = 0;
+  // one SO_ML step of the mixed-layer warp on the published profile (flags of buffer q)
+  auto ml_one = [&](int q) {
+    // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
+    bool bad = ibox[8 * q + 4] != 0;
+    const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
+    if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
+    const bool sorted = rt::ballot(bad) == 0;
+    if (PIPE) {
+      pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+      if (Ln == 0) dbox[0] = ml.bs[0];
+    } else {
+      pm::MlState tmp;
+      pm::ml_unpark(tmp, mlp, scan_s);
+      pm::ml_step(tmp, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+      pm::ml_park(tmp, mlp, false);
+      if (Ln == 0) dbox[0] = tmp.bs[0];
+    }
+  };
+  auto ml_phase1 = [&](long long it, int q) {  // SO_ML of the previous iteration + the flags this iteration publishes
+    if (it > 0) ml_one(q);
+    if (Ln == 0) {  // (last read in the previous iteration)
+      int* f = ibox + 8 * (q ^ 1);
+      f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
+    }
+  };
   for (long long it = 0; it < a.nsteps; ++it, p ^= 1) {
-    if (col) {
-      // bottom boundary condition and bottom-boundary-layer kappa (run_JansenNadeau_2018.py:233-254);
-      // every thread evaluates the switches from the published values
-      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
-      int vb = var_b, vn = var_n;
-      if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
-      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
-      else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
+    // ---------------------------------------------------------------- phase 1
+    double gb1 = 0.;   // thread 0: gradient of basin cell 1-2 (kept for the deferred bottom levels)
+    // the basin's kappa profile hangs on bs[0] of the SO_ML step still running (block-uniform: every thread,
+    // the mixed-layer warp included, evaluates it from the published values)
+    const bool late = (psi_so1 >= 0 && res_b1 > 0 && bne[0] < bbp[1] && M.basin.nvar > 1) || a.force_late != 0;
+    if (PIPE && mlw) {
+      ml_phase1(it, p);
+    } else {
+      // what the switches need apart from bs[0] (run_JansenNadeau_2018.py:233-254); every thread evaluates them
+      // from the published values
+      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol];
+      int vn = var_n;
       if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
       else { bbot_n = nb1; vn = 0; }
-      if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
-        status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
-      if (M.basin.nvar < 2) vb = 0;
       if (M.north.nvar < 2) vn = 0;
-      if (vb != var_b) {  // the owner re-reads its levels of the other variant
-        var_b = vb;
+      int vb = psi_so1 < 0 ? 1 : 0;  // (exact unless late; then phase 2 decides)
+      if (M.basin.nvar < 2) vb = 0;
+      auto load_variant_b = [&](int v) {  // the owner re-reads its levels of the other variant
+        var_b = v;
         PM_UNROLL
         for (int j = 0; j < LPT; ++j) {
           const int i = lo + j, s = j * kWideCol + t;
           if (i < nz) {
-            nwb[s] = vb ? nwb1[i] : nwb0[i];
-            kb[s] = (i >= 1 && i < nz - 1) ? kapb[(vb ? nvb : 0) + i] : 0.0;
+            nwb[s] = v ? nwb1[i] : nwb0[i];
+            kb[s] = (i >= 1 && i < nz - 1) ? kapb[(v ? nvb : 0) + i] : 0.0;
           }
         }
-      }
+      };
+      if (!late && vb != var_b) load_variant_b(vb);
       if (vn != var_n) {
         var_n = vn;
         PM_UNROLL
@@ -589,10 +639,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
           }
         }
       }
-      if (t == 0) {  // column.py:232
-        bb[0] = bbot_b;
-        bn[0] = bbot_n;
-      }
+      if (t == 0) bn[0] = bbot_n;  // column.py:232 (the basin's bottom value waits for bs[0]: phase 2)
       double gpb = 0., gpn = 0.;  // gradient of the cell below the current level
       if (lo >= 1 && lo < nz) {
         const double vb_ = adj(bbx[lo - 1], lo - 1, cvb, bs_b, n2_b, zcb);
@@ -607,14 +654,14 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
       }
       // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact.  No level tests: at
       // the boundary and padding levels -weff = kappa = 0 and every operand is finite, so b + dt*0 = b.
-      auto step = [&](auto UA) {
-        constexpr bool ua = decltype(UA)::value;
+      // BASIN: both columns (false: the northern one only); thread 0 leaves basin levels 0 and 1 to phase 2.
+      auto step = [&](auto UA, auto BASIN) {
+        constexpr bool ua = decltype(UA)::value, basin = decltype(BASIN)::value;
         PM_UNROLL
         for (int j = 0; j < LPT; ++j) {
           const int s = j * kWideCol + t;
           const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
           const double upn = j + 1 < LPT ? bn[j + 1 < LPT ? j + 1 : j] : un;
-          const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
           const double gn = pm::div_const(upn - bn[j], dzu[j], rdzu[j]);
           const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
           double Ai_b = A_b, rAi_b = rA_b, Ai_n = A_n, rAi_n = rA_n;
@@ -622,11 +669,17 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
             const int i = lo + j < nz ? lo + j : nz - 1;
             Ai_b = Ab[i]; rAi_b = rab[i]; Ai_n = An[i]; rAi_n = ran[i];
           }
-          {
-            const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
-            const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
-            const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
-            bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
+          if (basin) {
+            const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+            if (j >= 2 || t != 0) {
+              const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+              const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+              const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
+              bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
+            } else if (j == 1) {
+              gb1 = gb;
+            }
+            gpb = gb;
           }
           {
             const double bzz = pm::div_const(gn - gpn, dzc, rdzc[j]);
@@ -634,36 +687,85 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
             const double adv = pm::div_const(nw * sel, Ai_n, rAi_n);
             bn[j] = bn[j] + dt * (adv + kn[s] * bzz);
           }
-          gpb = gb;
           gpn = gn;
         }
       };
-      if (uniA)
-        step(std::true_type{});
-      else
-        step(std::false_type{});
+      if (!late) {
+        if (uniA) step(std::true_type{}, std::true_type{});
+        else step(std::false_type{}, std::true_type{});
+      } else {
+        if (uniA) step(std::true_type{}, std::false_type{});
+        else step(std::false_type{}, std::false_type{});
+      }
+      if (!PIPE && mlw) ml_phase1(it, p);
     }
-    rt::syncblock();  // every neighbour value of this step has been read
-    publish(p ^ 1);
-    rt::syncblock();
-    if (mlw) {
-      // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
-      bool bad = ibox[8 * (p ^ 1) + 4] != 0;
-      const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
-      if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
-      const bool sorted = rt::ballot(bad) == 0;
-      pm::MlState ml;
-      pm::ml_unpark(ml, mlp, scan_s);
-      pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
-      pm::ml_park(ml, mlp, false);
-      if (Ln == 0) {
-        dbox[0] = ml.bs[0];
-        int* f = ibox + 8 * p;  // read during this step; refilled by the publish of the next one
-        f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
+    rt::syncblock();  // SO_ML of the previous iteration is done; every neighbour value of this step has been read
+    // ---------------------------------------------------------------- phase 2
+    if (col) {
+      // the switches as the script writes them, now that bs[0] is known
+      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
+      int vb = var_b;
+      if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
+      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
+      else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
+      if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
+        status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
+      if (M.basin.nvar < 2) vb = 0;
+      if (late) {
+        // the whole basin column, serially after SO_ML (the values the neighbours need are still the published ones)
+        if (vb != var_b) {
+          var_b = vb;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j, s = j * kWideCol + t;
+            if (i < nz) {
+              nwb[s] = vb ? nwb1[i] : nwb0[i];
+              kb[s] = (i >= 1 && i < nz - 1) ? kapb[(vb ? nvb : 0) + i] : 0.0;
+            }
+          }
+        }
+        const int* f = ibox + 8 * p;
+        const bool cvb = f[0] != 0;
+        const double zcb = z[f[2] >= 0 ? f[2] : 0];
+        auto adjb = [&](double v, int i) {
+          if (cvb) return v > bs_b ? bs_b + n2_b * (z[i] - zcb) : v;
+          return i == nz - 1 ? bs_b : v;
+        };
+        if (t == 0) bb[0] = bbot_b;
+        double gpb = 0.;
+        if (lo >= 1 && lo < nz) gpb = pm::div_const(bb[0] - adjb(bbx[lo - 1], lo - 1), dzu_m, rdzu_m);
+        const double ub = lo + LPT < nz ? adjb(bbx[lo + LPT], lo + LPT) : 0.;
+        PM_UNROLL
+        for (int j = 0; j < LPT; ++j) {
+          const int s = j * kWideCol + t;
+          const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
+          const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+          const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
+          const int i = lo + j < nz ? lo + j : nz - 1;
+          const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+          const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+          const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[i], uniA ? rA_b : rab[i]);
+          bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
+          gpb = gb;
+        }
+      } else if (t == 0) {
+        // basin levels 0 and 1 (column.py:232, 235-249): b[0] = bbot, then level 1 with the kept gradient above it
+        bb[0] = bbot_b;
+        const double g0 = pm::div_const(bb[1] - bb[0], dzu[0], rdzu[0]);
+        const double dzc = 0.5 * (dzu[1] + dzu[0]);
+        const double bzz = pm::div_const(gb1 - g0, dzc, rdzc[1]);
+        const int s = 1 * kWideCol + 0;
+        const double nw = nwb[s], sel = nw > 0 ? gb1 : g0;
+        const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[1], uniA ? rA_b : rab[1]);
+        bb[1] = bb[1] + dt * (adv + kb[s] * bzz);
       }
     }
+    if (late) rt::syncblock();  // the serial basin step read the published neighbour values: only now overwrite them
+    if (col) publish(p ^ 1);
     rt::syncblock();
   }
+  if (mlw && a.nsteps > 0) ml_one(p);  // SO_ML of the last iteration
+  rt::syncblock();
 
   bool nan = false;
   if (col) {
@@ -678,8 +780,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideAll, 1) k_wide_steps2(WideArgs a) {
     }
   }
   if (mlw) {
-    pm::MlState ml;
-    pm::ml_unpark(ml, mlp, scan_s);
+    if (!PIPE) pm::ml_unpark(ml, mlp, scan_s);
     PM_UNROLL
     for (int e = 0; e < pm::kMLP; ++e) {
       const int k = pm::mlk(e);
@@ -729,6 +830,7 @@ int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, in
   a.memb = a.geo + 4 * (size_t)m->nz;
   a.it0 = it0;
   a.nsteps = 0;
+  a.force_late = std::getenv("PMOC_WIDE_FORCE_LATE") != nullptr;
   const long long K = m->K, it_end = it0 + nsteps;
   const size_t sm_r = wide_refresh_smem(m->nz, m->ny, m->nb);
   if (sm_r > 227 * 1024) return fail(PMOC_EUNSUPPORTED, "nz too large for shared memory");
@@ -744,11 +846,11 @@ int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, in
     a.nsteps = stop - ii;
     int rc;
     if (m->nz <= 4 * kWideCol)
-      rc = launch(k_wide_steps2<4, 2>, m->M, kWideAll, wide_steps2_smem(4, m->ny), stream, a);
+      rc = launch(k_wide_steps2<4, 2, true>, m->M, kWideCol + 32, wide_steps2_smem(4, m->ny), stream, a);
     else if (m->nz <= 8 * kWideCol)
-      rc = launch(k_wide_steps2<8, 3>, m->M, kWideAll, wide_steps2_smem(8, m->ny), stream, a);
+      rc = launch(k_wide_steps2<8, 3, true>, m->M, kWideCol + 32, wide_steps2_smem(8, m->ny), stream, a);
     else
-      rc = launch(k_wide_steps2<16, 4>, m->M, kWideAll, wide_steps2_smem(16, m->ny), stream, a);
+      rc = launch(k_wide_steps2<16, 4, false>, m->M, kWideCol, wide_steps2_smem(16, m->ny), stream, a);
     if (rc) return rc;
     ii = stop;
   }

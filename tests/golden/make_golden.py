@@ -423,3 +423,9 @@ if __name__ == '__main__':
                     [1, 720, 721, 1000])
   if want('c5_4096'):
     coupled_fixture('c5_4096.npz', configs.c5_single_global_basin(1, nz=4096, dt_days=0.01), [0], [1, 40])
+  # the same grid with the streamfunctions re-diagnosed every 20 iterations (MOC_up_iters is a free parameter of the
+  # script): the block-wide diagnosis kernel is exercised INSIDE a run at nz = 4096, three times in 45 steps
+  if want('c5_4096_k20'):
+    spec = configs.c5_single_global_basin(2, nz=4096, dt_days=0.01, axes=(2, 1, 1, 1))
+    spec.K = 20
+    coupled_fixture('c5_4096_k20.npz', spec, [0, 1], [20, 21, 45])

@@ -18,7 +18,7 @@ def emu():
 
 
 @pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 720), ('twocol', 480), ('c3', 480), ('c4', 600), ('c4_literal', 120),
-                                       ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40), ('twobasin', 480)])
+                                       ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40), ('c5_4096_k20', 45), ('twobasin', 480)])
 def test_fused_kernel_vs_reference(emu, name, nmax):
   run_against_golden(emu, name, nmax)
 
@@ -151,3 +151,21 @@ def test_host_handle_api(emu):
   assert lib.pmoc_host_open(None, ctypes.byref(ctypes.c_void_p())) == _abi.EINVAL
   b.close()
   assert lib.pmoc_host_close(None) == _abi.OK
+
+
+def test_wide_kernel_serial_schedule_is_bitwise_the_pipelined_one(emu, monkeypatch):
+  """Block-per-member step kernel: the pipelined schedule (SO_ML one step behind on its own warp, basin levels 0
+  and 1 finished once bs[0] is known) and the serial fall-back taken when the kappa choice hangs on bs[0] must give
+  the same bits; the fall-back is forced through the library's test hook."""
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  spec = configs.c5_single_global_basin(2, nz=320, dt_days=1., axes=(2, 1, 1, 1))
+  a = Ensemble(spec, backend=emu)
+  a.run(730)
+  monkeypatch.setenv('PMOC_WIDE_FORCE_LATE', '1')
+  b = Ensemble(spec, backend=emu)
+  b.run(730)
+  for k, v in a.state().items():
+    assert np.array_equal(v, b.state()[k]), k
+  for k in ('Psi_iso_b', 'Psi_so', 'bbot_basin', 'Psi_s'):
+    assert np.array_equal(a.diagnostics()[k], b.diagnostics()[k]), k

@@ -24,7 +24,8 @@ def cuda():
 
 
 @pytest.mark.parametrize('name,nmax', [('c1', 1200), ('c2', 2160), ('twocol', 480), ('c3', 2400), ('c4', 2400),
-                                       ('c4_literal', 1200), ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40), ('twobasin', 1200)])
+                                       ('c4_literal', 1200), ('c5', 480), ('c5_wide', 1000), ('c5_4096', 40), ('c5_4096_k20', 45),
+                                       ('twobasin', 1200)])
 def test_fused_kernel_vs_reference(cuda, name, nmax):
   worst = run_against_golden(cuda, name, nmax)
   print('%s: worst relative error %.2e' % (name, worst))

@@ -17,7 +17,7 @@ from oracle import pymoc_oracle as O
 warnings.filterwarnings('ignore', category=RuntimeWarning)
 
 COUPLED = [('c1', 300), ('c2', 73), ('twocol', 25), ('c3', 25), ('c3_bvp', 25), ('c4', 13), ('c4_literal', 120),
-           ('c5', 25), ('twobasin', 25)]
+           ('c5', 25), ('twobasin', 25), ('c5_4096_k20', 21)]
 
 
 @pytest.mark.parametrize('name,nmax', COUPLED)
