@@ -9,6 +9,7 @@ STATUS_NAMES = {1: 'EINVAL', 2: 'EUNSUPPORTED', 3: 'ECUDA', 4: 'ENODEVICE'}
 HAS_NORTH, HAS_TW, ISO, HAS_SO, HAS_ML, ORDER_JN, SO_BVP, HAS_PAC = 1, 2, 4, 8, 16, 32, 64, 128
 STAGE_CONVECT, STAGE_VERTADVDIFF, STAGE_HORADV = 1, 2, 4
 IO_STATE, IO_PSI, IO_DIAG = 1, 2, 4
+MAX_NZ_WARP, MAX_NZ_WIDE, MAX_NY_ML = 256, 4096, 64  # PMOC_MAX_* of the header
 ST_NAN, ST_BS_NONMONOTONE, ST_BRENT_SIGN, ST_XP_NONMONOTONE, ST_ML_INDEX, ST_BVP_SERIES, ST_NOISE_SWITCH = 1, 2, 4, 8, 16, 32, 64
 ST_TIE_CELL, ST_BS_SAWTOOTH = 128, 256
 ST_PARITY_UNDEFINED = ST_BS_NONMONOTONE | ST_NOISE_SWITCH | ST_TIE_CELL  # the reference's own result hangs on rounding noise

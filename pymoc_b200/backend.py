@@ -38,6 +38,11 @@ class CudaBackend:
   def sync(self):
     self.torch.cuda.synchronize(self.device)
 
+  def guard(self):
+    """Context in which this backend's device is the current CUDA device: the library launches on the current
+    device, so a backend built for another device must switch to it around every call."""
+    return self.torch.cuda.device(self.device)
+
 
 class PinnedHostBackend:
   """Pinned HOST buffers for the host-pointer entry points of the C ABI (``pmoc_model_run_host``,
@@ -79,3 +84,7 @@ class PinnedHostBackend:
 
   def sync(self):
     pass
+
+  def guard(self):
+    import contextlib
+    return contextlib.nullcontext()

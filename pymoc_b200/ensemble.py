@@ -203,14 +203,22 @@ class Ensemble:
   def diagnose(self):
     """Diagnose every streamfunction from the current state (the scripts' pre-loop
     ``AMOC.solve(); AMOC.Psibz(); SO.solve()``)."""
-    _abi.check(self.lib, self.lib.pmoc_model_diagnose(ctypes.byref(self.model), self.be.stream()))
+    with self._guard():
+      _abi.check(self.lib, self.lib.pmoc_model_diagnose(ctypes.byref(self.model), self.be.stream()))
     self._diagnosed = True
+
+  def _guard(self):
+    """The backend's device made current around a library call (backends without one: no-op)."""
+    import contextlib
+    g = getattr(self.be, 'guard', None)
+    return g() if g is not None else contextlib.nullcontext()
 
   def run(self, nsteps, sync=True):
     """Advance every member by ``nsteps`` loop iterations (one fused kernel launch)."""
     if self.spec.order == 'post' and not self._diagnosed:
       self.diagnose()
-    _abi.check(self.lib, self.lib.pmoc_model_run(ctypes.byref(self.model), self.it, int(nsteps), self.be.stream()))
+    with self._guard():
+      _abi.check(self.lib, self.lib.pmoc_model_run(ctypes.byref(self.model), self.it, int(nsteps), self.be.stream()))
     self.it += int(nsteps)
     if sync:
       self.be.sync()

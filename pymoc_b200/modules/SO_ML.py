@@ -37,6 +37,10 @@ class SO_ML(object):
     pb = np.ascontiguousarray(Psi_b, dtype=np.float64)
     if not np.any(pb != 0):
       np.nonzero(pb)[0][0]  # the reference's IndexError (SO_ML.py:229)
+    if y.size > _abi.MAX_NY_ML or bb.size > _abi.MAX_NZ_WARP:
+      raise ValueError('pymoc_b200.modules.SO_ML: the per-method kernel takes ny <= %d surface points and nz <= %d levels '
+                       '(got %d, %d); larger models run through pymoc_b200.ensemble.Ensemble'
+                       % (_abi.MAX_NY_ML, _abi.MAX_NZ_WARP, y.size, bb.size))
     c = Call()
     m = _abi.Model()
     m.M, m.nz, m.ny = 1, bb.size, y.size

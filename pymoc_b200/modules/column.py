@@ -4,7 +4,8 @@ Same constructor keywords and defaults (column.py:19-29), same attributes, same 
 mutation of ``self.b`` (column.py:231-232,249,268,271,312), same exceptions.  Every
 ``timestep`` / ``vertadvdiff`` / ``convect`` / ``horadv`` call samples the callables on the
 grid on the host and runs ``pmoc_column_timestep`` (include/pymoc_b200.h).  The equilibrium
-solver (``solve_equi``/``ode``/``bc``) is outside the time-stepping hot path and not provided.
+solver (``solve_equi``/``ode``/``bc``) is outside the time-stepping hot path: a host-side utility
+that, like the reference, hands its one boundary value problem to ``scipy.integrate.solve_bvp``.
 """
 import numpy as np
 
@@ -38,14 +39,39 @@ class Column(object):
       raise ImportError('You need NumPy version 1.13.0 or later. Please upgrade your NumPy libary.')
     return np.gradient(self.Akappa(z), z)
 
+  # --- equilibrium profile (column.py:124-208).  Not time stepping: one two-point
+  # boundary value problem per call, which the reference hands to scipy.integrate.solve_bvp.  It is a host-side
+  # set-up utility here as well (same solver, same ODE, same boundary residuals), for API completeness
+  # (examples/example_iteration.py:63); nothing on the GPU path calls it.
+  def bc(self, ya, yb):
+    """Boundary residuals: bottom buoyancy (or its gradient when ``bzbot`` is given) and surface buoyancy."""
+    if self.bzbot is None:
+      return np.array([ya[0] - self.bbot, yb[0] - self.bs])
+    return np.array([ya[1] - self.bzbot, yb[0] - self.bs])
+
+  def ode(self, z, y):
+    """b' = y1;  y1' = (wA - d(A kappa)/dz) / (A kappa) * y1  (steady advection-diffusion, column.py:155-185)."""
+    return np.vstack((y[1], (self.wA(z) - self.dAkappa_dz(z)) / self.Akappa(z) * y[1]))
+
   def solve_equi(self, wA):
-    raise NotImplementedError('pymoc_b200 covers the time-stepping path; the equilibrium BVP '
-                              '(column.py:187-208) is out of scope')
+    """Equilibrium buoyancy profile for the area-integrated velocity ``wA`` (column.py:187-208).  Like the
+    reference it REBINDS ``self.b`` / ``self.bz`` to new arrays."""
+    from scipy import integrate
+    self.wA = make_func(wA, self.z, 'w')
+    guess = np.zeros((2, np.size(self.z)))
+    guess[0, :] = self.b
+    guess[1, :] = self.bz
+    res = integrate.solve_bvp(self.ode, self.bc, self.z, guess)
+    self.b = res.sol(self.z)[0, :]
+    self.bz = res.sol(self.z)[1, :]
 
   # --- the GPU call ---------------------------------------------------------------------------
   def _run(self, stages, wA=None, dt=1., do_conv=False, vdx_in=None, b_in=None):
     z = np.ascontiguousarray(self.z, dtype=np.float64)
     nz = z.size
+    if nz > _abi.MAX_NZ_WARP:
+      raise ValueError('pymoc_b200.modules.Column: the per-method kernels hold one column per warp, nz <= %d (got %d); '
+                       'taller columns run through pymoc_b200.ensemble.Ensemble' % (_abi.MAX_NZ_WARP, nz))
     c = Call()
     col = _abi.Column()
     dev_b = c.dev(np.asarray(self.b, dtype=np.float64).reshape(1, nz))
@@ -79,10 +105,13 @@ class Column(object):
 
   def timestep(self, wA=0., dt=1., do_conv=False, vdx_in=None, b_in=None):
     stages = _abi.STAGE_VERTADVDIFF | (_abi.STAGE_CONVECT if do_conv else 0)
-    if vdx_in is not None:
-      if b_in is None:
-        raise TypeError('b_in is needed if vdx_in is provided')
+    missing = vdx_in is not None and b_in is None
+    if vdx_in is not None and not missing:
       stages |= _abi.STAGE_HORADV
       vdx_in = make_array(vdx_in, self.z, 'vdx_in')
       b_in = make_array(b_in, self.z, 'b_in')
+    else:
+      vdx_in = b_in = None
     self._run(stages, wA=make_array(wA, self.z, 'wA'), dt=dt, do_conv=do_conv, vdx_in=vdx_in, b_in=b_in)
+    if missing:  # like the reference, AFTER convect + vertadvdiff have changed self.b (column.py:336-348)
+      raise TypeError('b_in is needed if vdx_in is provided')

@@ -35,6 +35,9 @@ class Psi_SO(object):
   def _kernel(self, b_profile):
     z = np.ascontiguousarray(self.z, dtype=np.float64)
     y = np.ascontiguousarray(self.y, dtype=np.float64)
+    if z.size > _abi.MAX_NZ_WARP:
+      raise ValueError('pymoc_b200.modules.Psi_SO: the per-method kernels hold one column per warp, nz <= %d (got %d); '
+                       'taller columns run through pymoc_b200.ensemble.Ensemble' % (_abi.MAX_NZ_WARP, z.size))
     c = Call()
     m = _abi.Model()
     m.M, m.nz, m.ny = 1, z.size, y.size
@@ -77,6 +80,44 @@ class Psi_SO(object):
     """Psi_GM in m^3/s (psi_SO.py:277-331); like the reference it needs ``self.Psi_Ek``."""
     z = np.asarray(self.z, dtype=np.float64)
     return self._kernel(self.b(z) + 0 * z)[2] * 1e6
+
+  # --- host-side pieces of the reference's method surface (state-independent or O(nz) set-up arithmetic; the
+  # kernels evaluate the same expressions inside pmoc_so_solve) -----------------------------------------------
+  def calc_N2(self):
+    """Buoyancy frequency N^2(z) as a callable (psi_SO.py:142-162): centred differences over the two adjacent
+    cells in the interior, one-sided at the two ends; used by the F2010 smoother (``c`` given)."""
+    z = np.asarray(self.z, dtype=np.float64)
+    b = self.b(z)
+    h = z[1:] - z[:-1]
+    n2 = np.empty(z.size)
+    n2[1:-1] = (b[2:] - b[:-2]) / (h[1:] + h[:-1])
+    n2[0] = (b[1] - b[0]) / h[0]
+    n2[-1] = (b[-1] - b[-2]) / h[-1]
+    return make_func(n2, self.z, 'N2')
+
+  def calc_bottom_taper(self, H, z):
+    """Quadratic taper over the lowest ``H`` metres (psi_SO.py:164-187); the scalar 1. when ``H`` is None."""
+    if H is None:
+      return 1.
+    return 1. - np.maximum(z[0] + H - z, 0.)**2. / H**2.
+
+  def calc_top_taper(self, H, z, scalar=True):
+    """Quadratic taper over the uppermost ``H`` metres (psi_SO.py:189-216).  With ``H`` None: the scalar 1., or
+    (``scalar=False``, the Ekman taper) ones with a zero at the surface."""
+    if H is not None:
+      return 1 - np.maximum(z + H, 0)**2. / H**2.
+    if scalar:
+      return 1.
+    ones = np.ones(np.size(z))
+    ones[-1] = 0.
+    return ones
+
+  def bc_GM(self, ya, yb):
+    """Boundary residuals of the F2010 smoother (psi_SO.py:245-275): Psi_GM = -Psi_Ek at both ends when
+    ``bvp_with_Ek`` (needs ``self.Psi_Ek`` in Sv, as in the reference), zero otherwise."""
+    if self.bvp_with_Ek:
+      return np.array([ya[0] + self.Psi_Ek[0] * 1e6, yb[0] + self.Psi_Ek[-1] * 1e6])
+    return np.array([ya[0], yb[0]])
 
   def update(self, b=None, bs=None):
     if b is not None:

@@ -25,8 +25,19 @@ class Psi_Thermwind(object):
     # kept for signature compatibility; the closed-form solve needs no initial guess
     self.sol_init = np.zeros((2, nz)) if sol_init is None else sol_init
 
+  # the reference's formulation of the problem (psi_thermwind.py:72-123), kept for callers that hand it to their
+  # own solver; ``solve`` uses the closed form
+  def bc(self, ya, yb):
+    return np.array([ya[0], yb[0]])
+
+  def ode(self, z, y):
+    return np.vstack((y[1], 1. / self.f * (self.b2(z) - self.b1(z))))
+
   def _profiles(self):
     z = np.ascontiguousarray(self.z, dtype=np.float64)
+    if z.size > _abi.MAX_NZ_WARP:
+      raise ValueError('pymoc_b200.modules.Psi_Thermwind: the per-method kernels hold one column per warp, nz <= %d '
+                       '(got %d); taller columns run through pymoc_b200.ensemble.Ensemble' % (_abi.MAX_NZ_WARP, z.size))
     ones = 0 * z + 1.
     return z, np.asarray(self.b1(z) * ones, dtype=np.float64), np.asarray(self.b2(z) * ones, dtype=np.float64)
 

@@ -46,3 +46,7 @@ class EmuBackend:
 
   def sync(self):
     pass
+
+  def guard(self):
+    import contextlib
+    return contextlib.nullcontext()

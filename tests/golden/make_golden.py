@@ -391,6 +391,22 @@ if __name__ == '__main__':
     print('units done', flush=True)
     if 'units' in sys.argv[1:]:
       sys.exit(0)
+  if want('equi'):  # Column.solve_equi as examples/example_iteration.py:63 calls it (three outer iterations)
+    A, bs, bbot = 8e13, 0.03, -0.0004
+    z = np.asarray(np.linspace(-3500, 0, 70))
+    kappa = lambda zz: 1e-5 + 3e-5 * np.exp(zz / 100) + 3e-4 * np.exp(-zz / 1000 - 4)
+    b0 = bs * np.exp(z / 300.) + z / z[0] * bbot
+    amoc = Psi_Thermwind(z=z, b1=b0)
+    amoc.solve()
+    basin = Column(z=z, kappa=kappa, Area=A, b=b0.copy(), bs=bs, bbot=bbot)
+    out = {}
+    for it in range(3):
+      basin.solve_equi(amoc.Psi * 1e6)
+      out[str(it)] = dict(wA=amoc.Psi * 1e6, b=basin.b.copy(), bz=basin.bz.copy())
+      amoc.update(b1=0.8 * amoc.b1(z) + 0.2 * basin.b)
+      amoc.solve()
+    save_tree(os.path.join(HERE, 'equi.npz'), dict(versions=VERSIONS, z=z, b0=b0, A=A, bs=bs, bbot=bbot, iters=out))
+    print('equi done', flush=True)
   if want('c1'):
     GAP = check_callable_sampling()
     coupled_fixture('c1.npz', configs.c1_timestepping(1), [0], [1, 2, 10, 300, 1200], extra=dict(callable_init_gap=GAP))

@@ -84,9 +84,12 @@ def column_reference_tests():
   c2.vertadvdiff(wA=wA, dt=dt)
   c2.horadv(vdx_in=vdx_in, b_in=b_in, dt=dt)
   assert all(c1.b == c2.b)
+  c3, c4 = mk(), mk()
   with pytest.raises(TypeError) as e:
-    mk().timestep(wA=wA, dt=dt, vdx_in=vdx_in)
+    c3.timestep(wA=wA, dt=dt, vdx_in=vdx_in)
   assert str(e.value) == 'b_in is needed if vdx_in is provided'
+  c4.vertadvdiff(wA=wA, dt=dt)  # the reference raises AFTER the column has been stepped (column.py:336-348)
+  assert all(c3.b == c4.b)
 
 
 def column_golden_units():
@@ -279,3 +282,56 @@ def psib_edge_cases():
     check('classes on the levels', z, ba, 0.5 * ba, pr, nb=nz)
     c = ba.copy(); c[7] = c[8]
     check('flat cell on a class', z, c, 0.5 * ba, pr, nb=nz)
+
+
+# ------------------------------------------------------------------- host-side method surface
+def host_api_checks():
+  """Methods of the reference classes that do no time stepping (host arithmetic here as there)."""
+  # tests/modules/test_psi_SO.py:135-142: linear b -> constant N2, 10 decimals
+  z = np.asarray(np.linspace(-4000, 0, 80))
+  y = np.asarray(np.linspace(0, 2.0e6, 51))
+  so = Psi_SO(z=z, y=y, b=np.linspace(0.03, -0.001, 80), bs=0.05, tau=0.12)
+  n2 = (so.b(z[1]) - so.b(z[0])) / (z[1] - z[0])
+  f = so.calc_N2()
+  assert all(np.round(f(zz), decimals=10) == np.round(n2, decimals=10) for zz in z)
+  # non-uniform grid: the centred / one-sided differences of psi_SO.py:154-160
+  zn = -4000. * (1. - np.linspace(0, 1, 41)**0.7)
+  zn[-1] = 0.
+  bn = 0.02 * np.exp(zn / 500.)
+  so2 = Psi_SO(z=zn, y=y, b=bn, bs=0.05, tau=0.12)
+  want = np.zeros(zn.size)
+  h = zn[1:] - zn[:-1]
+  want[1:-1] = (bn[2:] - bn[:-2]) / (h[1:] + h[:-1])
+  want[0], want[-1] = (bn[1] - bn[0]) / h[0], (bn[-1] - bn[-2]) / h[-1]
+  assert np.array_equal(so2.calc_N2()(zn), want)
+  # tapers (psi_SO.py:164-216)
+  assert so.calc_bottom_taper(None, z) == 1. and so.calc_top_taper(None, z) == 1.
+  ek = so.calc_top_taper(None, z, scalar=False)
+  assert ek.shape == z.shape and ek[-1] == 0. and np.all(ek[:-1] == 1.)
+  bt = so.calc_bottom_taper(1000., z)
+  assert bt[0] == 0. and np.all(bt[z >= z[0] + 1000.] == 1.) and np.all(np.diff(bt) >= 0)
+  assert np.array_equal(bt, 1. - np.maximum(z[0] + 1000. - z, 0.)**2. / 1000.**2.)
+  tt = so.calc_top_taper(500., z)
+  assert tt[-1] == 0. and np.all(tt[z <= -500.] == 1.)
+  # bc_GM (psi_SO.py:270-275)
+  so.Psi_Ek = np.linspace(1., 2., 80)
+  assert np.array_equal(so.bc_GM(np.array([3., 9.]), np.array([4., 9.])), np.array([3., 4.]))
+  so.bvp_with_Ek = True
+  assert np.array_equal(so.bc_GM(np.array([3., 9.]), np.array([4., 9.])), np.array([3. + 1e6, 4. + 2e6]))
+  # Column.bc / ode / solve_equi against the reference's own runs (golden equi.npz, examples/example_iteration.py)
+  t = golden('equi')
+  zc = t['z']
+  kappa = lambda zz: 1e-5 + 3e-5 * np.exp(zz / 100) + 3e-4 * np.exp(-zz / 1000 - 4)
+  col = Column(z=zc, kappa=kappa, Area=float(t['A']), b=t['b0'].copy(), bs=float(t['bs']), bbot=float(t['bbot']))
+  assert np.array_equal(col.bc(np.array([1., 2.]), np.array([3., 4.])), np.array([1. - col.bbot, 3. - col.bs]))
+  alias = col.b
+  for it in sorted(t['iters']):
+    d = t['iters'][it]
+    col.solve_equi(d['wA'])
+    assert relmax(col.b, d['b']) < 1e-12 and relmax(col.bz, d['bz']) < 1e-12, it
+  assert col.b is not alias  # rebinds, like the reference (column.py:207-208)
+  col.bzbot = 1e-7
+  assert np.array_equal(col.bc(np.array([1., 2.]), np.array([3., 4.])), np.array([2. - 1e-7, 3. - col.bs]))
+  tw = Psi_Thermwind(z=zc, b1=t['b0'], b2=0.)
+  assert np.array_equal(tw.bc(np.array([1., 2.]), np.array([3., 4.])), np.array([1., 3.]))
+  assert np.array_equal(tw.ode(zc[:3], np.ones((2, 3)))[1], 1. / tw.f * (0. - t['b0'][:3]))

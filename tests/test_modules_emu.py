@@ -41,6 +41,10 @@ def test_psib_edge_cases():
   mc.psib_edge_cases()
 
 
+def test_host_side_method_surface():
+  mc.host_api_checks()
+
+
 def test_dropin_example_script_matches_batched_engine():
   """examples/twocol_plusSO_dropin.py (the reference script's loop over the drop-in classes, one launch per
   method call) ends where the fused kernel ends for the same member."""
