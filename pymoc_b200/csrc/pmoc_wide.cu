@@ -555,165 +555,238 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideCol + (PIPE ? 32 : 0), 1) k_wide_steps2(Wid
   rt::syncblock();
 
   int p = 0;
-  // one SO_ML step of the mixed-layer warp on the published profile (flags of buffer q)
-  auto ml_one = [&](int q) {
-    // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
-    bool bad = ibox[8 * q + 4] != 0;
-    const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
-    if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
-    const bool sorted = rt::ballot(bad) == 0;
-    if (PIPE) {
-      pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
-      if (Ln == 0) dbox[0] = ml.bs[0];
-    } else {
-      pm::MlState tmp;
-      pm::ml_unpark(tmp, mlp, scan_s);
-      pm::ml_step(tmp, bbx, pm_s, nz, sorted, bs_s, dt, &status);
-      pm::ml_park(tmp, mlp, false);
-      if (Ln == 0) dbox[0] = tmp.bs[0];
-    }
-  };
-  auto ml_phase1 = [&](long long it, int q) {  // SO_ML of the previous iteration + the flags this iteration publishes
-    if (it > 0) ml_one(q);
-    if (Ln == 0) {  // (last read in the previous iteration)
-      int* f = ibox + 8 * (q ^ 1);
-      f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
-    }
-  };
-  for (long long it = 0; it < a.nsteps; ++it, p ^= 1) {
-    // ---------------------------------------------------------------- phase 1
-    double gb1 = 0.;   // thread 0: gradient of basin cell 1-2 (kept for the deferred bottom levels)
-    // the basin's kappa profile hangs on bs[0] of the SO_ML step still running (block-uniform: every thread,
-    // the mixed-layer warp included, evaluates it from the published values)
-    const bool late = (psi_so1 >= 0 && res_b1 > 0 && bne[0] < bbp[1] && M.basin.nvar > 1) || a.force_late != 0;
-    if (PIPE && mlw) {
-      ml_phase1(it, p);
-    } else {
-      // what the switches need apart from bs[0] (run_JansenNadeau_2018.py:233-254); every thread evaluates them
-      // from the published values
-      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol];
-      int vn = var_n;
-      if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
-      else { bbot_n = nb1; vn = 0; }
-      if (M.north.nvar < 2) vn = 0;
-      int vb = psi_so1 < 0 ? 1 : 0;  // (exact unless late; then phase 2 decides)
-      if (M.basin.nvar < 2) vb = 0;
-      auto load_variant_b = [&](int v) {  // the owner re-reads its levels of the other variant
-        var_b = v;
-        PM_UNROLL
-        for (int j = 0; j < LPT; ++j) {
-          const int i = lo + j, s = j * kWideCol + t;
-          if (i < nz) {
-            nwb[s] = v ? nwb1[i] : nwb0[i];
-            kb[s] = (i >= 1 && i < nz - 1) ? kapb[(v ? nvb : 0) + i] : 0.0;
-          }
-        }
-      };
-      if (!late && vb != var_b) load_variant_b(vb);
-      if (vn != var_n) {
-        var_n = vn;
-        PM_UNROLL
-        for (int j = 0; j < LPT; ++j) {
-          const int i = lo + j, s = j * kWideCol + t;
-          if (i < nz) {
-            nwn[s] = vn ? nwn1[i] : nwn0[i];
-            kn[s] = (i >= 1 && i < nz - 1) ? kapn[(vn ? nvn : 0) + i] : 0.0;
-          }
-        }
+  if constexpr (PIPE) {
+    // one SO_ML step of the mixed-layer warp on the published profile (flags of buffer q)
+    auto ml_one = [&](int q) {
+      // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
+      bool bad = ibox[8 * q + 4] != 0;
+      const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
+      if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
+      const bool sorted = rt::ballot(bad) == 0;
+      if (PIPE) {
+        pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+        if (Ln == 0) dbox[0] = ml.bs[0];
+      } else {
+        pm::MlState tmp;
+        pm::ml_unpark(tmp, mlp, scan_s);
+        pm::ml_step(tmp, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+        pm::ml_park(tmp, mlp, false);
+        if (Ln == 0) dbox[0] = tmp.bs[0];
       }
-      // convective adjustment (column.py:264-271) of the own levels and of the two neighbour values
-      const int* f = ibox + 8 * p;
-      const bool cvb = f[0] != 0, cvn = f[1] != 0;
-      const double zcb = z[f[2] >= 0 ? f[2] : 0], zcn = z[f[3] >= 0 ? f[3] : 0];
-      auto adj = [&](double v, int i, bool cv, double bs, double n2, double zc) {
-        if (cv) return v > bs ? bs + n2 * (z[i] - zc) : v;
-        return i == nz - 1 ? bs : v;
-      };
-      if ((cvb && mine_b) || (cvn && mine_n) || owns_top) {
-        PM_UNROLL
-        for (int j = 0; j < LPT; ++j) {
-          const int i = lo + j;
-          if (i < nz) {
-            bb[j] = adj(bb[j], i, cvb, bs_b, n2_b, zcb);
-            bn[j] = adj(bn[j], i, cvn, bs_n, n2_n, zcn);
-          }
-        }
+    };
+    auto ml_phase1 = [&](long long it, int q) {  // SO_ML of the previous iteration + the flags this iteration publishes
+      if (it > 0) ml_one(q);
+      if (Ln == 0) {  // (last read in the previous iteration)
+        int* f = ibox + 8 * (q ^ 1);
+        f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
       }
-      if (t == 0) bn[0] = bbot_n;  // column.py:232 (the basin's bottom value waits for bs[0]: phase 2)
-      double gpb = 0., gpn = 0.;  // gradient of the cell below the current level
-      if (lo >= 1 && lo < nz) {
-        const double vb_ = adj(bbx[lo - 1], lo - 1, cvb, bs_b, n2_b, zcb);
-        const double vn_ = adj(bne[2 * (t - 1) + 1], lo - 1, cvn, bs_n, n2_n, zcn);
-        gpb = pm::div_const(bb[0] - vb_, dzu_m, rdzu_m);
-        gpn = pm::div_const(bn[0] - vn_, dzu_m, rdzu_m);
-      }
-      double ub = 0., un = 0.;  // level above the thread's last one
-      if (lo + LPT < nz) {
-        ub = adj(bbx[lo + LPT], lo + LPT, cvb, bs_b, n2_b, zcb);
-        un = adj(bne[2 * (t + 1)], lo + LPT, cvn, bs_n, n2_n, zcn);
-      }
-      // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact.  No level tests: at
-      // the boundary and padding levels -weff = kappa = 0 and every operand is finite, so b + dt*0 = b.
-      // BASIN: both columns (false: the northern one only); thread 0 leaves basin levels 0 and 1 to phase 2.
-      auto step = [&](auto UA, auto BASIN) {
-        constexpr bool ua = decltype(UA)::value, basin = decltype(BASIN)::value;
-        PM_UNROLL
-        for (int j = 0; j < LPT; ++j) {
-          const int s = j * kWideCol + t;
-          const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
-          const double upn = j + 1 < LPT ? bn[j + 1 < LPT ? j + 1 : j] : un;
-          const double gn = pm::div_const(upn - bn[j], dzu[j], rdzu[j]);
-          const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
-          double Ai_b = A_b, rAi_b = rA_b, Ai_n = A_n, rAi_n = rA_n;
-          if (!ua) {
-            const int i = lo + j < nz ? lo + j : nz - 1;
-            Ai_b = Ab[i]; rAi_b = rab[i]; Ai_n = An[i]; rAi_n = ran[i];
-          }
-          if (basin) {
-            const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
-            if (j >= 2 || t != 0) {
-              const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
-              const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
-              const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
-              bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
-            } else if (j == 1) {
-              gb1 = gb;
+    };
+    for (long long it = 0; it < a.nsteps; ++it, p ^= 1) {
+      // ---------------------------------------------------------------- phase 1
+      double gb1 = 0.;   // thread 0: gradient of basin cell 1-2 (kept for the deferred bottom levels)
+      // the basin's kappa profile hangs on bs[0] of the SO_ML step still running (block-uniform: every thread,
+      // the mixed-layer warp included, evaluates it from the published values)
+      const bool late = (psi_so1 >= 0 && res_b1 > 0 && bne[0] < bbp[1] && M.basin.nvar > 1) || a.force_late != 0;
+      if (PIPE && mlw) {
+        ml_phase1(it, p);
+      } else {
+        // what the switches need apart from bs[0] (run_JansenNadeau_2018.py:233-254); every thread evaluates them
+        // from the published values
+        const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol];
+        int vn = var_n;
+        if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
+        else { bbot_n = nb1; vn = 0; }
+        if (M.north.nvar < 2) vn = 0;
+        int vb = psi_so1 < 0 ? 1 : 0;  // (exact unless late; then phase 2 decides)
+        if (M.basin.nvar < 2) vb = 0;
+        auto load_variant_b = [&](int v) {  // the owner re-reads its levels of the other variant
+          var_b = v;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j, s = j * kWideCol + t;
+            if (i < nz) {
+              nwb[s] = v ? nwb1[i] : nwb0[i];
+              kb[s] = (i >= 1 && i < nz - 1) ? kapb[(v ? nvb : 0) + i] : 0.0;
             }
+          }
+        };
+        if (!late && vb != var_b) load_variant_b(vb);
+        if (vn != var_n) {
+          var_n = vn;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j, s = j * kWideCol + t;
+            if (i < nz) {
+              nwn[s] = vn ? nwn1[i] : nwn0[i];
+              kn[s] = (i >= 1 && i < nz - 1) ? kapn[(vn ? nvn : 0) + i] : 0.0;
+            }
+          }
+        }
+        // convective adjustment (column.py:264-271) of the own levels and of the two neighbour values
+        const int* f = ibox + 8 * p;
+        const bool cvb = f[0] != 0, cvn = f[1] != 0;
+        const double zcb = z[f[2] >= 0 ? f[2] : 0], zcn = z[f[3] >= 0 ? f[3] : 0];
+        auto adj = [&](double v, int i, bool cv, double bs, double n2, double zc) {
+          if (cv) return v > bs ? bs + n2 * (z[i] - zc) : v;
+          return i == nz - 1 ? bs : v;
+        };
+        if ((cvb && mine_b) || (cvn && mine_n) || owns_top) {
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j;
+            if (i < nz) {
+              bb[j] = adj(bb[j], i, cvb, bs_b, n2_b, zcb);
+              bn[j] = adj(bn[j], i, cvn, bs_n, n2_n, zcn);
+            }
+          }
+        }
+        if (t == 0) bn[0] = bbot_n;  // column.py:232 (the basin's bottom value waits for bs[0]: phase 2)
+        double gpb = 0., gpn = 0.;  // gradient of the cell below the current level
+        if (lo >= 1 && lo < nz) {
+          const double vb_ = adj(bbx[lo - 1], lo - 1, cvb, bs_b, n2_b, zcb);
+          const double vn_ = adj(bne[2 * (t - 1) + 1], lo - 1, cvn, bs_n, n2_n, zcn);
+          gpb = pm::div_const(bb[0] - vb_, dzu_m, rdzu_m);
+          gpn = pm::div_const(bn[0] - vn_, dzu_m, rdzu_m);
+        }
+        double ub = 0., un = 0.;  // level above the thread's last one
+        if (lo + LPT < nz) {
+          ub = adj(bbx[lo + LPT], lo + LPT, cvb, bs_b, n2_b, zcb);
+          un = adj(bne[2 * (t + 1)], lo + LPT, cvn, bs_n, n2_n, zcn);
+        }
+        // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact.  No level tests: at
+        // the boundary and padding levels -weff = kappa = 0 and every operand is finite, so b + dt*0 = b.
+        // BASIN: both columns (false: the northern one only); thread 0 leaves basin levels 0 and 1 to phase 2.
+        auto step = [&](auto UA, auto BASIN) {
+          constexpr bool ua = decltype(UA)::value, basin = decltype(BASIN)::value;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int s = j * kWideCol + t;
+            const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
+            const double upn = j + 1 < LPT ? bn[j + 1 < LPT ? j + 1 : j] : un;
+            const double gn = pm::div_const(upn - bn[j], dzu[j], rdzu[j]);
+            const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
+            double Ai_b = A_b, rAi_b = rA_b, Ai_n = A_n, rAi_n = rA_n;
+            if (!ua) {
+              const int i = lo + j < nz ? lo + j : nz - 1;
+              Ai_b = Ab[i]; rAi_b = rab[i]; Ai_n = An[i]; rAi_n = ran[i];
+            }
+            if (basin) {
+              const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+              if (j >= 2 || t != 0) {
+                const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+                const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+                const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
+                bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
+              } else if (j == 1) {
+                gb1 = gb;
+              }
+              gpb = gb;
+            }
+            {
+              const double bzz = pm::div_const(gn - gpn, dzc, rdzc[j]);
+              const double nw = nwn[s], sel = nw > 0 ? gn : gpn;
+              const double adv = pm::div_const(nw * sel, Ai_n, rAi_n);
+              bn[j] = bn[j] + dt * (adv + kn[s] * bzz);
+            }
+            gpn = gn;
+          }
+        };
+        if (!late) {
+          if (uniA) step(std::true_type{}, std::true_type{});
+          else step(std::false_type{}, std::true_type{});
+        } else {
+          if (uniA) step(std::true_type{}, std::false_type{});
+          else step(std::false_type{}, std::false_type{});
+        }
+        if (!PIPE && mlw) ml_phase1(it, p);
+      }
+      rt::syncblock();  // SO_ML of the previous iteration is done; every neighbour value of this step has been read
+      // ---------------------------------------------------------------- phase 2
+      if (col) {
+        // the switches as the script writes them, now that bs[0] is known
+        const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
+        int vb = var_b;
+        if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
+        if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
+        else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
+        if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
+          status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
+        if (M.basin.nvar < 2) vb = 0;
+        if (late) {
+          // the whole basin column, serially after SO_ML (the values the neighbours need are still the published ones)
+          if (vb != var_b) {
+            var_b = vb;
+            PM_UNROLL
+            for (int j = 0; j < LPT; ++j) {
+              const int i = lo + j, s = j * kWideCol + t;
+              if (i < nz) {
+                nwb[s] = vb ? nwb1[i] : nwb0[i];
+                kb[s] = (i >= 1 && i < nz - 1) ? kapb[(vb ? nvb : 0) + i] : 0.0;
+              }
+            }
+          }
+          const int* f = ibox + 8 * p;
+          const bool cvb = f[0] != 0;
+          const double zcb = z[f[2] >= 0 ? f[2] : 0];
+          auto adjb = [&](double v, int i) {
+            if (cvb) return v > bs_b ? bs_b + n2_b * (z[i] - zcb) : v;
+            return i == nz - 1 ? bs_b : v;
+          };
+          if (t == 0) bb[0] = bbot_b;
+          double gpb = 0.;
+          if (lo >= 1 && lo < nz) gpb = pm::div_const(bb[0] - adjb(bbx[lo - 1], lo - 1), dzu_m, rdzu_m);
+          const double ub = lo + LPT < nz ? adjb(bbx[lo + LPT], lo + LPT) : 0.;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int s = j * kWideCol + t;
+            const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
+            const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+            const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
+            const int i = lo + j < nz ? lo + j : nz - 1;
+            const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+            const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+            const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[i], uniA ? rA_b : rab[i]);
+            bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
             gpb = gb;
           }
-          {
-            const double bzz = pm::div_const(gn - gpn, dzc, rdzc[j]);
-            const double nw = nwn[s], sel = nw > 0 ? gn : gpn;
-            const double adv = pm::div_const(nw * sel, Ai_n, rAi_n);
-            bn[j] = bn[j] + dt * (adv + kn[s] * bzz);
-          }
-          gpn = gn;
+        } else if (t == 0) {
+          // basin levels 0 and 1 (column.py:232, 235-249): b[0] = bbot, then level 1 with the kept gradient above it
+          bb[0] = bbot_b;
+          const double g0 = pm::div_const(bb[1] - bb[0], dzu[0], rdzu[0]);
+          const double dzc = 0.5 * (dzu[1] + dzu[0]);
+          const double bzz = pm::div_const(gb1 - g0, dzc, rdzc[1]);
+          const int s = 1 * kWideCol + 0;
+          const double nw = nwb[s], sel = nw > 0 ? gb1 : g0;
+          const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[1], uniA ? rA_b : rab[1]);
+          bb[1] = bb[1] + dt * (adv + kb[s] * bzz);
         }
-      };
-      if (!late) {
-        if (uniA) step(std::true_type{}, std::true_type{});
-        else step(std::false_type{}, std::true_type{});
-      } else {
-        if (uniA) step(std::true_type{}, std::false_type{});
-        else step(std::false_type{}, std::false_type{});
       }
-      if (!PIPE && mlw) ml_phase1(it, p);
+      if (late) rt::syncblock();  // the serial basin step read the published neighbour values: only now overwrite them
+      if (col) publish(p ^ 1);
+      rt::syncblock();
     }
-    rt::syncblock();  // SO_ML of the previous iteration is done; every neighbour value of this step has been read
-    // ---------------------------------------------------------------- phase 2
-    if (col) {
-      // the switches as the script writes them, now that bs[0] is known
-      const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
-      int vb = var_b;
-      if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
-      if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
-      else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
-      if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
-        status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
-      if (M.basin.nvar < 2) vb = 0;
-      if (late) {
-        // the whole basin column, serially after SO_ML (the values the neighbours need are still the published ones)
-        if (vb != var_b) {
+    if (mlw && a.nsteps > 0) ml_one(p);  // SO_ML of the last iteration
+    rt::syncblock();
+
+  } else {
+    // sixteen levels per thread: the serial schedule (columns, barrier, publish, barrier, SO_ML on the last column warp,
+    // barrier) -- the deferral logic of the pipelined form costs registers this variant does not have
+    for (long long it = 0; it < a.nsteps; ++it, p ^= 1) {
+      if (col) {
+        // bottom boundary condition and bottom-boundary-layer kappa (run_JansenNadeau_2018.py:233-254);
+        // every thread evaluates the switches from the published values
+        const double bb0 = bbp[0], bb1 = bbp[1], nb0 = bne[0], nb1 = bne[2 * kWideCol], bs0 = dbox[0];
+        int vb = var_b, vn = var_n;
+        if (psi_so1 < 0) { bbot_b = bs0; vb = 1; }
+        if (res_b1 > 0 && nb0 < bb1 && nb0 < bs0) { bbot_b = nb0; vb = 1; }
+        else if (psi_so1 >= 0) { bbot_b = bb1; vb = 0; }
+        if (res_n1 < 0 && bb0 < nb1) { bbot_n = bb0; vn = 1; }
+        else { bbot_n = nb1; vn = 0; }
+        if (noise != 0 && ((noise & 1u) || ((noise & 2u) && nb0 < bb1 && nb0 < bs0) || ((noise & 4u) && bb0 < nb1)))
+          status |= PMOC_ST_NOISE_SWITCH;  // the outcome hung on the sign of a noise value
+        if (M.basin.nvar < 2) vb = 0;
+        if (M.north.nvar < 2) vn = 0;
+        if (vb != var_b) {  // the owner re-reads its levels of the other variant
           var_b = vb;
           PM_UNROLL
           for (int j = 0; j < LPT; ++j) {
@@ -724,49 +797,112 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(kWideCol + (PIPE ? 32 : 0), 1) k_wide_steps2(Wid
             }
           }
         }
-        const int* f = ibox + 8 * p;
-        const bool cvb = f[0] != 0;
-        const double zcb = z[f[2] >= 0 ? f[2] : 0];
-        auto adjb = [&](double v, int i) {
-          if (cvb) return v > bs_b ? bs_b + n2_b * (z[i] - zcb) : v;
-          return i == nz - 1 ? bs_b : v;
-        };
-        if (t == 0) bb[0] = bbot_b;
-        double gpb = 0.;
-        if (lo >= 1 && lo < nz) gpb = pm::div_const(bb[0] - adjb(bbx[lo - 1], lo - 1), dzu_m, rdzu_m);
-        const double ub = lo + LPT < nz ? adjb(bbx[lo + LPT], lo + LPT) : 0.;
-        PM_UNROLL
-        for (int j = 0; j < LPT; ++j) {
-          const int s = j * kWideCol + t;
-          const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
-          const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
-          const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
-          const int i = lo + j < nz ? lo + j : nz - 1;
-          const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
-          const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
-          const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[i], uniA ? rA_b : rab[i]);
-          bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
-          gpb = gb;
+        if (vn != var_n) {
+          var_n = vn;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j, s = j * kWideCol + t;
+            if (i < nz) {
+              nwn[s] = vn ? nwn1[i] : nwn0[i];
+              kn[s] = (i >= 1 && i < nz - 1) ? kapn[(vn ? nvn : 0) + i] : 0.0;
+            }
+          }
         }
-      } else if (t == 0) {
-        // basin levels 0 and 1 (column.py:232, 235-249): b[0] = bbot, then level 1 with the kept gradient above it
-        bb[0] = bbot_b;
-        const double g0 = pm::div_const(bb[1] - bb[0], dzu[0], rdzu[0]);
-        const double dzc = 0.5 * (dzu[1] + dzu[0]);
-        const double bzz = pm::div_const(gb1 - g0, dzc, rdzc[1]);
-        const int s = 1 * kWideCol + 0;
-        const double nw = nwb[s], sel = nw > 0 ? gb1 : g0;
-        const double adv = pm::div_const(nw * sel, uniA ? A_b : Ab[1], uniA ? rA_b : rab[1]);
-        bb[1] = bb[1] + dt * (adv + kb[s] * bzz);
+        // convective adjustment (column.py:264-271) of the own levels and of the two neighbour values
+        const int* f = ibox + 8 * p;
+        const bool cvb = f[0] != 0, cvn = f[1] != 0;
+        const double zcb = z[f[2] >= 0 ? f[2] : 0], zcn = z[f[3] >= 0 ? f[3] : 0];
+        auto adj = [&](double v, int i, bool cv, double bs, double n2, double zc) {
+          if (cv) return v > bs ? bs + n2 * (z[i] - zc) : v;
+          return i == nz - 1 ? bs : v;
+        };
+        if ((cvb && mine_b) || (cvn && mine_n) || owns_top) {
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int i = lo + j;
+            if (i < nz) {
+              bb[j] = adj(bb[j], i, cvb, bs_b, n2_b, zcb);
+              bn[j] = adj(bn[j], i, cvn, bs_n, n2_n, zcn);
+            }
+          }
+        }
+        if (t == 0) {  // column.py:232
+          bb[0] = bbot_b;
+          bn[0] = bbot_n;
+        }
+        double gpb = 0., gpn = 0.;  // gradient of the cell below the current level
+        if (lo >= 1 && lo < nz) {
+          const double vb_ = adj(bbx[lo - 1], lo - 1, cvb, bs_b, n2_b, zcb);
+          const double vn_ = adj(bne[2 * (t - 1) + 1], lo - 1, cvn, bs_n, n2_n, zcn);
+          gpb = pm::div_const(bb[0] - vb_, dzu_m, rdzu_m);
+          gpn = pm::div_const(bn[0] - vn_, dzu_m, rdzu_m);
+        }
+        double ub = 0., un = 0.;  // level above the thread's last one
+        if (lo + LPT < nz) {
+          ub = adj(bbx[lo + LPT], lo + LPT, cvb, bs_b, n2_b, zcb);
+          un = adj(bne[2 * (t + 1)], lo + LPT, cvn, bs_n, n2_n, zcn);
+        }
+        // bit-faithful explicit step (column.py:235-249), see pm::col_step_exact.  No level tests: at
+        // the boundary and padding levels -weff = kappa = 0 and every operand is finite, so b + dt*0 = b.
+        auto step = [&](auto UA) {
+          constexpr bool ua = decltype(UA)::value;
+          PM_UNROLL
+          for (int j = 0; j < LPT; ++j) {
+            const int s = j * kWideCol + t;
+            const double upb = j + 1 < LPT ? bb[j + 1 < LPT ? j + 1 : j] : ub;
+            const double upn = j + 1 < LPT ? bn[j + 1 < LPT ? j + 1 : j] : un;
+            const double gb = pm::div_const(upb - bb[j], dzu[j], rdzu[j]);
+            const double gn = pm::div_const(upn - bn[j], dzu[j], rdzu[j]);
+            const double dzc = 0.5 * (dzu[j] + (j > 0 ? dzu[j > 0 ? j - 1 : 0] : dzu_m));
+            double Ai_b = A_b, rAi_b = rA_b, Ai_n = A_n, rAi_n = rA_n;
+            if (!ua) {
+              const int i = lo + j < nz ? lo + j : nz - 1;
+              Ai_b = Ab[i]; rAi_b = rab[i]; Ai_n = An[i]; rAi_n = ran[i];
+            }
+            {
+              const double bzz = pm::div_const(gb - gpb, dzc, rdzc[j]);
+              const double nw = nwb[s], sel = nw > 0 ? gb : gpb;
+              const double adv = pm::div_const(nw * sel, Ai_b, rAi_b);
+              bb[j] = bb[j] + dt * (adv + kb[s] * bzz);
+            }
+            {
+              const double bzz = pm::div_const(gn - gpn, dzc, rdzc[j]);
+              const double nw = nwn[s], sel = nw > 0 ? gn : gpn;
+              const double adv = pm::div_const(nw * sel, Ai_n, rAi_n);
+              bn[j] = bn[j] + dt * (adv + kn[s] * bzz);
+            }
+            gpb = gb;
+            gpn = gn;
+          }
+        };
+        if (uniA)
+          step(std::true_type{});
+        else
+          step(std::false_type{});
       }
+      rt::syncblock();  // every neighbour value of this step has been read
+      publish(p ^ 1);
+      rt::syncblock();
+      if (mlw) {
+        // b_basin sorted?  inside the threads and warps: flagged by publish; across the warps: here
+        bool bad = ibox[8 * (p ^ 1) + 4] != 0;
+        const int e = (Ln + 1) * 32 * LPT;  // first level of the next warp
+        if (Ln < kWideCol / 32 - 1 && e < nz) bad |= !(bbx[e] >= bbx[e - 1]);
+        const bool sorted = rt::ballot(bad) == 0;
+        pm::MlState ml;
+        pm::ml_unpark(ml, mlp, scan_s);
+        pm::ml_step(ml, bbx, pm_s, nz, sorted, bs_s, dt, &status);
+        pm::ml_park(ml, mlp, false);
+        if (Ln == 0) {
+          dbox[0] = ml.bs[0];
+          int* f = ibox + 8 * p;  // read during this step; refilled by the publish of the next one
+          f[0] = 0; f[1] = 0; f[2] = -1; f[3] = -1; f[4] = 0;
+        }
+      }
+      rt::syncblock();
     }
-    if (late) rt::syncblock();  // the serial basin step read the published neighbour values: only now overwrite them
-    if (col) publish(p ^ 1);
-    rt::syncblock();
-  }
-  if (mlw && a.nsteps > 0) ml_one(p);  // SO_ML of the last iteration
-  rt::syncblock();
 
+  }
   bool nan = false;
   if (col) {
     PM_UNROLL
