@@ -52,7 +52,7 @@ from pymoc_b200 import configs  # noqa: E402
 
 WORKLOADS = {
     # name: (builder(M) -> spec, default members per GPU, default model steps per bench step)
-    'C1': (lambda M: configs.c1_timestepping(M), 16384, 3000),
+    'C1': (lambda M: configs.c1_timestepping(M), 65536, 3000),
     'C2': (lambda M: configs.c2_column_so(M), 65536, 7200),
     'twocol': (lambda M: configs.twocol(M), 32768, 2400),
     'C3': (lambda M: configs.c3_twocol_so(M), 32768, 2400),
@@ -65,7 +65,7 @@ WORKLOADS = {
     'C5_4096': (lambda M: configs.c5_single_global_basin(M, nz=4096, dt_days=0.01, kapfac_max=1.), 16384, 720),
 }
 # workloads timed next to the headline one (same process, CUDA events): name -> members per GPU in that role
-EXTRAS = {'C3': 32768, 'C3_bvp': 32768, 'C4': 32768, 'C5_4096': 2048, 'C1': 16384}
+EXTRAS = {'C3': 32768, 'C3_bvp': 32768, 'C4': 32768, 'C5_4096': 2048, 'C1': 65536}
 E2E_EXTRAS = ('C3_bvp',)  # the north-star model also gets an end-to-end figure
 
 

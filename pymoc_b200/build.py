@@ -23,7 +23,8 @@ NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', 
 
 def units():
   """(source, object name, extra defines)"""
-  out = [('pmoc_ops.cu', 'ops.o', []), ('pmoc_host.cu', 'host.o', []), ('pmoc_wide.cu', 'wide.o', [])]
+  out = [('pmoc_ops.cu', 'ops.o', []), ('pmoc_host.cu', 'host.o', []), ('pmoc_wide.cu', 'wide.o', []),
+         ('pmoc_twcol.cu', 'twcol.o', [])]
   out += [('pmoc_model.cu', 'model_%d.o' % n, ['-DPM_LPL=%d' % n]) for n in LPLS]
   return out
 

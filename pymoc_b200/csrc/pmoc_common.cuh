@@ -238,6 +238,10 @@ using namespace pmk;
 // block-per-member path for nz > PMOC_MAX_NZ_WARP (pmoc_wide.cu)
 int pmoc_run_model_wide(const pmoc_model* m, long long it0, long long nsteps, int diagnose_only, void* stream);
 
+// several members per warp for the column + thermal-wind topology (pmoc_twcol.cu)
+bool pmoc_twcol_supported(const pmoc_model* m);
+int pmoc_launch_twcol(const pmoc_model* m, long long it0, long long nsteps, int diagnose_only, void* stream);
+
 // one launcher per levels-per-lane, each in its own translation unit (pmoc_model.cu)
 #define PM_DECL_MODEL(n) int pmoc_launch_model_##n(const RunArgs& ra, void* stream);
 PM_DECL_MODEL(2) PM_DECL_MODEL(3) PM_DECL_MODEL(4) PM_DECL_MODEL(5) PM_DECL_MODEL(6) PM_DECL_MODEL(7) PM_DECL_MODEL(8)

@@ -1,6 +1,8 @@
 // Per-module kernels and the C-ABI entry points of pymoc_b200 (see include/pymoc_b200.h).
 #include "pmoc_common.cuh"
 
+#include <cstdlib>
+
 thread_local char pmoc_g_err[256] = "";
 
 namespace pmk {
@@ -287,6 +289,7 @@ int run_model(const pmoc_model* m, long long it0, long long nsteps, int diagnose
   if (nsteps < 0 || it0 < 0) return fail(PMOC_EINVAL, "negative it0 / nsteps");
   if (!diagnose_only && nsteps == 0) return PMOC_OK;
   if (m->nz > PMOC_MAX_NZ_WARP) return pmoc_run_model_wide(m, it0, nsteps, diagnose_only, stream);
+  if (pmoc_twcol_supported(m) && !std::getenv("PMOC_NO_TWCOL")) return pmoc_launch_twcol(m, it0, nsteps, diagnose_only, stream);
   RunArgs ra;
   ra.m = *m;
   ra.m.flags &= ~PMOC_SO_BVP;

@@ -46,7 +46,7 @@ def build(force=False):
     return LIB
   cu = ['-x', 'c++']
   jobs = [(os.path.join(CSRC, 'pmoc_ops.cu'), 'ops.o', [], cu), (os.path.join(CSRC, 'pmoc_host.cu'), 'host.o', [], cu),
-          (os.path.join(CSRC, 'pmoc_wide.cu'), 'wide.o', [], cu),
+          (os.path.join(CSRC, 'pmoc_wide.cu'), 'wide.o', [], cu), (os.path.join(CSRC, 'pmoc_twcol.cu'), 'twcol.o', [], cu),
           (os.path.join(HERE, 'pmoc_emu.cpp'), 'emu.o', [], [])]
   jobs += [(os.path.join(CSRC, 'pmoc_model.cu'), 'model_%d.o' % n, ['-DPM_LPL=%d' % n], cu) for n in LPLS]
   with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:

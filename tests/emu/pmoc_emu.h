@@ -48,6 +48,9 @@ inline double shfl_up(double v, int d) { int l = lane(); return xchg(v, l >= d ?
 inline double shfl_down(double v, int d) { int l = lane(); return xchg(v, l + d < 32 ? l + d : l); }
 inline double shfl_xor(double v, int m) { return xchg(v, lane() ^ m); }
 inline int shfl_i(int v, int src) { return xchg(v, src); }
+inline double shfl_w(double v, int src, int w) { int l = lane(); return xchg(v, (l & ~(w - 1)) + (src & (w - 1))); }
+inline double shfl_up_w(double v, int d, int w) { int l = lane(), s = l & (w - 1); return xchg(v, s >= d ? l - d : l); }
+inline double shfl_down_w(double v, int d, int w) { int l = lane(), s = l & (w - 1); return xchg(v, s + d < w ? l + d : l); }
 inline unsigned ballot(bool p) {
   int v = p ? 1 : 0;
   const unsigned char* all = pmemu::exchange(&v, sizeof(int));

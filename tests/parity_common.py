@@ -251,3 +251,34 @@ def f2010_smoother_converged(backend, sizes=(46, 80, 200, 256), bvp_tol=1e-9, to
       worst = max(worst, relmax(got['Psi_GM'][m], gm))
   assert worst < tol, worst
   return worst
+
+
+def twcol_sizes(backend):
+  """The several-members-per-warp kernel of the column + thermal-wind topology (pmoc_twcol.cu): every group width /
+  levels-per-lane variant, member counts that leave groups and warps partly empty, K > 1, split launches bit for
+  bit, against the live oracle."""
+  import warnings
+
+  from oracle import pymoc_oracle as O
+  from pymoc_b200 import configs
+  warnings.filterwarnings('ignore')
+  worst = 0.0
+  for nz, M, K in ((24, 9, 1), (40, 5, 1), (56, 3, 2), (70, 7, 1), (73, 3, 1), (100, 3, 1), (128, 5, 7), (144, 2, 1)):
+    spec = configs.c1_timestepping(M, nz=nz)
+    spec.dt = spec.dt * min(1., (70. / nz)**2)  # the script's 60 days is diffusively stable up to nz ~ 78
+    spec.K = K
+    ens = Ensemble(spec, backend=backend)
+    ens.run(50)
+    got = {**ens.state(), **ens.diagnostics()}
+    cut = Ensemble(spec, backend=backend)
+    cut.run(13)
+    cut.run(37)
+    assert np.array_equal(cut.state()['b_basin'], got['b_basin']) and np.array_equal(cut.diagnostics()['Psi_tw'], got['Psi_tw'])
+    assert not got['status'].any()
+    for m in range(M):
+      want = O.run_coupled(spec.member_case(m), 50, O.REFERENCE)
+      for key in ('b_basin', 'Psi_tw'):
+        err = relmax(got[key][m], want[key])
+        worst = max(worst, err)
+        assert err < TOL, (nz, M, K, m, key, err)
+  return worst

@@ -169,3 +169,8 @@ def test_wide_kernel_serial_schedule_is_bitwise_the_pipelined_one(emu, monkeypat
     assert np.array_equal(v, b.state()[k]), k
   for k in ('Psi_iso_b', 'Psi_so', 'bbot_basin', 'Psi_s'):
     assert np.array_equal(a.diagnostics()[k], b.diagnostics()[k]), k
+
+
+def test_twcol_kernel_sizes_vs_live_oracle(emu):
+  from parity_common import twcol_sizes
+  twcol_sizes(emu)

@@ -176,7 +176,7 @@ def test_edge_sizes_vs_live_oracle(cuda):
 # Bench-lattice samples: seeded-random members of the very lattices bench.py steps,
 # every one against the live oracle; see parity_common.lattice_sample for the contract.
 @pytest.mark.parametrize('workload,M,nsample,nsteps,tol,max_flagged', [
-    ('C1', 16384, 64, 600, TOL, 0.02),
+    ('C1', 65536, 64, 600, TOL, 0.02),
     ('C2', 65536, 256, 600, TOL, 0.02),
     ('C3', 262144, 256, 600, TOL, 0.02),
     ('twobasin', 32768, 256, 600, TOL, 0.02),
@@ -231,3 +231,8 @@ def test_host_handle_matches_device_path(cuda):
         assert np.array_equal(dev.diagnostics()[key], ens.diagnostics()[key], equal_nan=True), (spec.name, key)
       assert np.array_equal(dev.diagnostics()['status'], ens.diagnostics()['status'])
       ens.close()
+
+
+def test_twcol_kernel_sizes_vs_live_oracle(cuda):
+  from parity_common import twcol_sizes
+  print('twcol sizes: worst relative error %.2e' % twcol_sizes(cuda))
