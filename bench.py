@@ -101,12 +101,14 @@ def algorithmic_flops(spec):
 #   flops: executed FP64 flops per member-step = (dadd + dmul + 2 dfma thread instructions) / member-steps of the launch
 #   dram: dram__bytes_read.sum + dram__bytes_write.sum per member of the launch (state and parameters are read once
 #         and state + diagnostics written once per launch, whatever the number of steps)
-NCU_FACTS = {
-    'C2': dict(pipe=60.7, flops=None, dram=(421.1e6 + 362.5e6) / 65536, source='profiles/r1final_full_summary.txt'),
-    'C3': dict(pipe=25.2, flops=None, dram=(232.2e6 + 386.6e6) / 32768, source='profiles/r1final_full_summary.txt'),
-    'C3_bvp': dict(pipe=28.9, flops=4313., dram=(233.9e6 + 656.7e6) / 32768, source='profiles/r2_C3_bvp.txt'),
-    'C4': dict(pipe=19.9, flops=None, dram=(257.4e6 + 478.5e6) / 32768, source='profiles/r1final_full_summary.txt'),
-    'C5_4096': dict(pipe=23.2, flops=None, dram=None, source='profiles/r1final_full_summary.txt'),
+NCU_FACTS = {  # round 2, profiles/r2_full_summary.txt (captures of the final kernels)
+    'C1': dict(pipe=58.3, flops=2164., dram=(147.76e6 + 28.69e6) / 65536, source='profiles/r2_full_summary.txt'),
+    'C2': dict(pipe=61.1, flops=1301., dram=(421.07e6 + 363.62e6) / 65536, source='profiles/r2_full_summary.txt'),
+    'C3': dict(pipe=25.2, flops=2106., dram=(233.15e6 + 389.19e6) / 32768, source='profiles/r2_full_summary.txt'),
+    'C3_bvp': dict(pipe=31.0, flops=4364., dram=(236.44e6 + 654.39e6) / 32768, source='profiles/r2_full_summary.txt'),
+    'C4': dict(pipe=20.6, flops=10121., dram=(256.84e6 + 414.28e6) / 32768, source='profiles/r2_full_summary.txt'),
+    # (block-per-member step kernel; its launches also read the per-member coefficient scratch)
+    'C5_4096': dict(pipe=23.7, flops=187792., dram=(870.51e6 + 603.98e6) / 2048, source='profiles/r2_full_summary.txt'),
 }
 
 

@@ -46,7 +46,7 @@ def launches(path):
     print('%-92s %6d %12.1f %6.1f%%' % (name, n, t / 1e3, 100 * t / total))
 
 
-def full(path, substr='', is_csv=False):
+def full(path, substr='', is_csv=False, member_steps=0):
   out = open(path).read() if is_csv else subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'],
                                                           capture_output=True, text=True).stdout
   rows = list(csv.reader(io.StringIO(out)))
@@ -64,10 +64,25 @@ def full(path, substr='', is_csv=False):
     print('  warp stall reasons (warps stalled per issue-active cycle):')
     for val, name in stalls[:8]:
       print('    %-40s %8.3f' % (name, val))
+    # executed FP64 work: thread-level DADD / DMUL / DFMA counts (per elapsed cycle, summed over the SM sub-partitions)
+    try:
+      op = lambda n: float(d['smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % n])
+      cyc = float(d['smsp__cycles_elapsed.avg'])
+      dadd, dmul, dfma = op('dadd'), op('dmul'), op('dfma')
+      flops = (dadd + dmul + 2 * dfma) * cyc
+      print('  executed FP64: DADD %.3e  DMUL %.3e  DFMA %.3e thread instructions -> %.4e flops in this launch'
+            % (dadd * cyc, dmul * cyc, dfma * cyc, flops))
+      print('  executed FP64 flops per cycle %.0f of 18944 (148 SM x 64 DFMA x 2) = %.1f %%' % (flops / cyc, flops / cyc / 189.44))
+      if member_steps:
+        print('  executed FP64 flops per member-step %.0f (%d member-steps in this launch)' % (flops / member_steps, member_steps))
+    except (KeyError, ValueError):
+      pass
 
 
 if __name__ == '__main__':
   if sys.argv[1] == 'launches':
     launches(sys.argv[2])
   else:
-    full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else '', is_csv=sys.argv[1] == 'raw')
+    # optional 4th argument: member-steps of the captured launch (members x steps), for the per-member-step flop count
+    full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else '', is_csv=sys.argv[1] == 'raw',
+         member_steps=int(sys.argv[4]) if len(sys.argv) > 4 else 0)

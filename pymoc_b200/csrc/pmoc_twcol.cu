@@ -85,10 +85,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
       const int sl = j * G + s;
-      const double weff = psi[j] * 1e6 - m_dak[sl];
-      const double dp = weff * m_pa[sl], dq = weff * m_qa[sl];
-      p[j] = weff < 0 ? m_pk[sl] - dp : m_pk[sl];
-      q[j] = weff < 0 ? m_qk[sl] : m_qk[sl] + dq;
+      const double weff = rt::fma(psi[j], 1e6, -m_dak[sl]);
+      const double dn = weff < 0 ? weff : 0.0, up = weff < 0 ? 0.0 : weff;  // upwind split (NaN goes to the q side)
+      p[j] = rt::fma(-dn, m_pa[sl], m_pk[sl]);
+      q[j] = rt::fma(up, m_qa[sl], m_qk[sl]);
     }
   };
   // Psi_Thermwind.solve for the current state
