@@ -162,21 +162,28 @@ def oracle_many(cases, nsteps, procs=None):
   import multiprocessing as mp
   import os
   procs = procs or min(len(cases), os.cpu_count() or 1)
+  os.environ.setdefault('OMP_NUM_THREADS', '1')  # (inherited by the workers: one BLAS thread each)
+  os.environ.setdefault('OPENBLAS_NUM_THREADS', '1')
   if procs <= 1:
     return [_oracle_task((c, nsteps)) for c in cases]
   with mp.get_context('spawn').Pool(procs) as pool:
     return pool.map(_oracle_task, [(c, nsteps) for c in cases], chunksize=1)
 
 
-def lattice_sample(backend, workload, M, nsample, nsteps, seed=0, tol=TOL, max_flagged=1.0, procs=None):
+def lattice_sample(backend, workload, M, nsample, nsteps, seed=0, tol=TOL, max_flagged=1.0, procs=None, K=None):
+  """``K``: override MOC_up_iters of the sampled members (a free parameter of the scripts), e.g. to cross several
+  diagnoses at nz = 4096, whose own K is 72 000."""
   from pymoc_b200 import _abi
   ms, cases = sample_cases(workload, M, nsample, seed)
+  if K is not None:
+    for c in cases:
+      c['K'] = int(K)
   ens = Ensemble(spec_from_cases(cases), backend=backend)
   ens.run(nsteps)
   got = {**ens.state(), **ens.diagnostics()}
   want = oracle_many(cases, nsteps, procs)
   st = got['status']
-  rep = dict(workload=workload, lattice=M, sampled=len(ms), steps=nsteps, census=_abi.status_census(st), worst_unflagged=0.0,
+  rep = dict(workload=workload, lattice=M, sampled=len(ms), steps=nsteps, K=int(cases[0]['K']), census=_abi.status_census(st), worst_unflagged=0.0,
              flagged_matching=0, flagged_missing=0, lost_by_both=0)
   for i, m in enumerate(ms):
     undefined = bool(st[i] & _abi.ST_PARITY_UNDEFINED)

@@ -236,3 +236,11 @@ def test_host_handle_matches_device_path(cuda):
 def test_twcol_kernel_sizes_vs_live_oracle(cuda):
   from parity_common import twcol_sizes
   print('twcol sizes: worst relative error %.2e' % twcol_sizes(cuda))
+
+
+def test_c5_4096_lattice_sample_across_diagnoses(cuda):
+  """BASELINE configs[4] (nz = 4096, block-per-member kernels): members of the 16,384-member bench lattice, with the
+  streamfunctions re-diagnosed every 20 iterations so that 45 steps cross three diagnoses, against the live oracle."""
+  from parity_common import lattice_sample
+  rep = lattice_sample(cuda, 'C5_4096', 16384, 6, 45, seed=5, K=20, max_flagged=0.2)
+  print('lattice sample %s' % rep)
