@@ -244,3 +244,23 @@ def test_c5_4096_lattice_sample_across_diagnoses(cuda):
   from parity_common import lattice_sample
   rep = lattice_sample(cuda, 'C5_4096', 16384, 6, 45, seed=5, K=20, max_flagged=0.2)
   print('lattice sample %s' % rep)
+
+
+def test_wide_kernel_serial_schedule_is_bitwise_the_pipelined_one(cuda, monkeypatch):
+  """Block-per-member step kernel (nz = 320 and 1 100: four and eight levels per thread, SO_ML on its own warp one step
+  behind the columns): the serial fall-back taken when the kappa choice hangs on bs[0], forced through the library's
+  test hook, gives the bits of the pipelined schedule."""
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  for nz, dt_days, n in ((320, 1., 730), (1100, 0.1, 300)):
+    spec = configs.c5_single_global_basin(64, nz=nz, dt_days=dt_days, kapfac_max=1.)
+    monkeypatch.delenv('PMOC_WIDE_FORCE_LATE', raising=False)
+    a = Ensemble(spec, backend=cuda)
+    a.run(n)
+    monkeypatch.setenv('PMOC_WIDE_FORCE_LATE', '1')
+    b = Ensemble(spec, backend=cuda)
+    b.run(n)
+    for k, v in a.state().items():
+      assert np.array_equal(v, b.state()[k], equal_nan=True), (nz, k)
+    for k in ('Psi_iso_b', 'Psi_so', 'bbot_basin', 'Psi_s'):
+      assert np.array_equal(a.diagnostics()[k], b.diagnostics()[k], equal_nan=True), (nz, k)
