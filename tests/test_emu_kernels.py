@@ -174,3 +174,24 @@ def test_wide_kernel_serial_schedule_is_bitwise_the_pipelined_one(emu, monkeypat
 def test_twcol_kernel_sizes_vs_live_oracle(emu):
   from parity_common import twcol_sizes
   twcol_sizes(emu)
+
+
+def test_host_loop_example_matches_device_path(emu, tmp_path):
+  """examples/jansen_nadeau_host_loop.py (the script's loop with diagnostics every Diag_iters iterations through the
+  persistent host-buffer handle) ends where one Ensemble.run of the same length ends, and writes the batched pickup."""
+  import importlib.util
+  import os
+
+  from pymoc_b200 import configs
+  from pymoc_b200.ensemble import Ensemble
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  spec_ = importlib.util.spec_from_file_location('host_loop_example', os.path.join(root, 'examples', 'jansen_nadeau_host_loop.py'))
+  mod = importlib.util.module_from_spec(spec_)
+  spec_.loader.exec_module(mod)
+  path = os.path.join(str(tmp_path), 'pickup.npz')
+  amoc = mod.main(4, 48, diag_iters=12, backend=emu, pickup_save=path)
+  assert amoc.shape == (4, 4) and np.isfinite(amoc).all()
+  ref = Ensemble(configs.c4_jansen_nadeau(4), backend=emu)
+  ref.run(48)
+  f = np.load(path)
+  assert np.array_equal(f['arr_0'], ref.state()['b_basin']) and np.array_equal(f['arr_2'], ref.state()['bs_ml'])
