@@ -38,3 +38,17 @@ def test_reference_arm_prints_one_json_line():
   assert d['impl'] == 'reference' and d['unit'] == 'member-timesteps/s' and d['value'] > 0
   assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1
   assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
+
+
+def test_both_arms_print_the_same_config_and_facts_are_consistent():
+  """`config` is a function of the command line and the workload definition only (the driver compares the two arms'),
+  and every ncu fact / extra workload names a workload that exists."""
+  import bench
+  from pymoc_b200 import configs
+  with configs.members(0, 1):
+    spec_a = bench.WORKLOADS['C3'][0](262144)
+  with configs.members(1000, 1001):
+    spec_b = bench.WORKLOADS['C3'][0](262144)
+  assert bench.config_of('C3', spec_a, 32768, 8, 2400) == bench.config_of('C3', spec_b, 32768, 8, 2400)
+  assert set(bench.NCU_FACTS) <= set(bench.WORKLOADS) and set(bench.EXTRAS) <= set(bench.WORKLOADS)
+  assert set(bench.E2E_EXTRAS) <= set(bench.EXTRAS)
