@@ -12,6 +12,8 @@
 // Columns with convection or a gradient bottom condition, other topologies and nz > 144 take the generic kernel.
 #include "pmoc_common.cuh"
 
+#include <type_traits>
+
 namespace pmk {
 
 struct TwColArgs {
@@ -79,20 +81,51 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
   const double rf = 1. / vat(M.tw_f, m);
   const double bs = vat(M.basin.bs, m), bbot = M.basin.bbot[m];
   const int top_s = (nz - 1) / LPL, top_j = (nz - 1) % LPL;
-
-  // folded stencil coefficients from the streamfunction in Sv (column.py:241-248, see pm::col_coeffs)
-  auto coeffs = [&](const double(&psi)[LPL]) {
+  // Uniform grid (every example: a linspace, spacing equal to 1e-13) and level-independent area: the geometry
+  // factors are scalars, (dt/A)/dzu = (dt/A)/dzd and dt kappa/(dzc dzu) = dt kappa/(dzc dzd), so a level reads two
+  // table words per step instead of ten (the kernel is otherwise bound by shared-memory reads: ncu
+  // short_scoreboard 2.2 warps per issue cycle).  Decided per warp; anything else takes the tabulated path.
+  const double h0 = M.z[1] - M.z[0];
+  bool odd = false;
+  {
+    const double* area = vrow(M.basin.Area, m);
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
-      const int sl = j * G + s;
+      const int i = s * LPL + j;
+      if (i < nz - 1) odd |= !(fabs(t_h[j * G + s] - h0) <= 1e-13 * fabs(h0));
+      if (i >= 1 && i < nz - 1) odd |= area[i] != area[1];
+    }
+  }
+  const bool fast = rt::ballot(odd) == 0 && nz >= 3;
+  const double u_hh = 0.5 * h0, u_a = h0 * h0 / 3., u_c = h0 * h0 / 6., u_rn = 1.0 / (double)(nz - 1);
+  const double u_pa = fast ? (dt / vrow(M.basin.Area, m)[1]) / h0 : 0.0;
+
+  // folded stencil coefficients from the streamfunction in Sv (column.py:241-248, see pm::col_coeffs)
+  auto coeffs_as = [&](const double(&psi)[LPL], auto FAST) {
+    constexpr bool fs = decltype(FAST)::value;
+    PM_UNROLL
+    for (int j = 0; j < LPL; ++j) {
+      const int i = s * LPL + j, sl = j * G + s;
       const double weff = rt::fma(psi[j], 1e6, -m_dak[sl]);
       const double dn = weff < 0 ? weff : 0.0, up = weff < 0 ? 0.0 : weff;  // upwind split (NaN goes to the q side)
-      p[j] = rt::fma(-dn, m_pa[sl], m_pk[sl]);
-      q[j] = rt::fma(up, m_qa[sl], m_qk[sl]);
+      if (fs) {
+        const bool in = i >= 1 && i < nz - 1;
+        const double k = m_pk[sl];  // (== m_qk on a uniform grid; zero outside the interior)
+        p[j] = in ? rt::fma(-dn, u_pa, k) : 0.0;
+        q[j] = in ? rt::fma(up, u_pa, k) : 0.0;
+      } else {
+        p[j] = rt::fma(-dn, m_pa[sl], m_pk[sl]);
+        q[j] = rt::fma(up, m_qa[sl], m_qk[sl]);
+      }
     }
   };
+  auto coeffs = [&](const double(&psi)[LPL]) {
+    if (fast) coeffs_as(psi, std::true_type{});
+    else coeffs_as(psi, std::false_type{});
+  };
   // Psi_Thermwind.solve for the current state
-  auto solve = [&](double(&psi)[LPL]) {
+  auto solve_as = [&](double(&psi)[LPL], auto FAST) {
+    constexpr bool fs = decltype(FAST)::value;
     double g[LPL], part[LPL];
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) g[j] = b2[j] - b[j];
@@ -102,7 +135,10 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     for (int j = 0; j < LPL; ++j) {  // Psi' by the trapezoid rule (exact: g is piecewise linear)
       const double gu = j < LPL - 1 ? g[j + 1 < LPL ? j + 1 : j] : gnext;
       part[j] = run;
-      run = rt::fma(t_hh[j * G + s], g[j] + gu, run);
+      if (fs)
+        run = (s * LPL + j < nz - 1) ? rt::fma(u_hh, g[j] + gu, run) : run;
+      else
+        run = rt::fma(t_hh[j * G + s], g[j] + gu, run);
     }
     double inc = run;
     PM_UNROLL
@@ -116,7 +152,11 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     for (int j = 0; j < LPL; ++j) {  // Psi: h I1 + h^2 (g_i / 3 + g_{i+1} / 6) per cell
       const int sl = j * G + s;
       const double gu = j < LPL - 1 ? g[j + 1 < LPL ? j + 1 : j] : gnext;
-      const double cell = rt::fma(t_h[sl], base1 + part[j], rt::fma(t_a[sl], g[j], t_c[sl] * gu));
+      double cell;
+      if (fs)
+        cell = (s * LPL + j < nz - 1) ? rt::fma(h0, base1 + part[j], rt::fma(u_a, g[j], u_c * gu)) : 0.0;
+      else
+        cell = rt::fma(t_h[sl], base1 + part[j], rt::fma(t_a[sl], g[j], t_c[sl] * gu));
       part[j] = run;
       run = run + cell;
     }
@@ -137,9 +177,14 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     PM_UNROLL
     for (int j = 0; j < LPL; ++j) {
       const int i = s * LPL + j;
-      const double x = rf * (part[j] - total * t_zf[j * G + s]);
+      const double zf = fs ? (double)i * u_rn : t_zf[j * G + s];
+      const double x = rf * (part[j] - total * zf);
       psi[j] = (i > 0 && i < nz - 1) ? pm::div_const(x, pm::kSv, 1.0 / pm::kSv) : 0.0;  // Psi(z0) = Psi(zN) = 0 exactly
     }
+  };
+  auto solve = [&](double(&psi)[LPL]) {
+    if (fast) solve_as(psi, std::true_type{});
+    else solve_as(psi, std::false_type{});
   };
   auto store_psi = [&](const double(&psi)[LPL]) {
     if (!live) return;

@@ -288,4 +288,27 @@ def twcol_sizes(backend):
         err = relmax(got[key][m], want[key])
         worst = max(worst, err)
         assert err < TOL, (nz, M, K, m, key, err)
+  # the tabulated path: a stretched grid, and a uniform grid with a level-dependent area (mixed with uniform members)
+  from pymoc_b200.spec import ColumnSpec, ModelSpec, ThermwindSpec
+  for which in ('stretched', 'area'):
+    nz, M = 60, 6
+    z = -3500. * (1. - np.linspace(0, 1, nz)**0.8) if which == 'stretched' else np.asarray(np.linspace(-3500, 0, nz))
+    z[-1] = 0.
+    kap = (1e-5 + 3e-5 * np.exp(z / 100) + 3e-4 * np.exp(-z / 1000 - 4))[None, :] * np.linspace(0.5, 1., M)[:, None]
+    area = np.full((M, nz), 8e13)
+    if which == 'area':
+      area[1::2] *= (1. + 0.3 * z / 3500.)[None, :]  # odd members: area shrinking with depth
+    dz_min = np.diff(z).min()
+    spec = ModelSpec(M=M, z=z, dt=0.3 * dz_min**2 / kap.max(), K=1,
+                     basin=ColumnSpec.build(z, kap, area, 0.03, 0.03 * np.exp(z / 300.) - 4e-4, bbot=-4e-4),
+                     tw=ThermwindSpec.build(z, f=1.2e-4, b2=0. * z), order='post', iso=False)
+    ens = Ensemble(spec, backend=backend)
+    ens.run(40)
+    got = {**ens.state(), **ens.diagnostics()}
+    for m in range(M):
+      want = O.run_coupled(spec.member_case(m), 40, O.REFERENCE)
+      for key in ('b_basin', 'Psi_tw'):
+        err = relmax(got[key][m], want[key])
+        worst = max(worst, err)
+        assert err < TOL, (which, m, key, err)
   return worst
