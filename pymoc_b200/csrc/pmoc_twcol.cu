@@ -78,7 +78,7 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     }
   }
   rt::syncwarp();
-  const double rf = 1. / vat(M.tw_f, m);
+  const double rf_sv = 1e-6 / vat(M.tw_f, m);
   const double bs = vat(M.basin.bs, m), bbot = M.basin.bbot[m];
   const int top_s = (nz - 1) / LPL, top_j = (nz - 1) % LPL;
   // Uniform grid (every example: a linspace, spacing equal to 1e-13) and level-independent area: the geometry
@@ -178,8 +178,8 @@ PM_GLOBAL void PM_LAUNCH_BOUNDS(128, 4) k_twcol(TwColArgs a) {
     for (int j = 0; j < LPL; ++j) {
       const int i = s * LPL + j;
       const double zf = fs ? (double)i * u_rn : t_zf[j * G + s];
-      const double x = rf * (part[j] - total * zf);
-      psi[j] = (i > 0 && i < nz - 1) ? pm::div_const(x, pm::kSv, 1.0 / pm::kSv) : 0.0;  // Psi(z0) = Psi(zN) = 0 exactly
+      const double x = rf_sv * rt::fma(-total, zf, part[j]);  // in Sv (rf_sv = 1e-6 / f)
+      psi[j] = (i > 0 && i < nz - 1) ? x : 0.0;  // Psi(z0) = Psi(zN) = 0 exactly
     }
   };
   auto solve = [&](double(&psi)[LPL]) {
