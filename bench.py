@@ -102,7 +102,7 @@ def algorithmic_flops(spec):
 #   dram: dram__bytes_read.sum + dram__bytes_write.sum per member of the launch (state and parameters are read once
 #         and state + diagnostics written once per launch, whatever the number of steps)
 NCU_FACTS = {  # round 2, profiles/r2_full_summary.txt (captures of the final kernels)
-    'C1': dict(pipe=58.3, flops=2164., dram=(147.76e6 + 28.69e6) / 65536, source='profiles/r2_full_summary.txt'),
+    'C1': dict(pipe=51.7, flops=2029., dram=(147.67e6 + 27.82e6) / 65536, source='profiles/r2_full_summary.txt'),
     'C2': dict(pipe=61.1, flops=1301., dram=(421.07e6 + 363.62e6) / 65536, source='profiles/r2_full_summary.txt'),
     'C3': dict(pipe=25.2, flops=2106., dram=(233.15e6 + 389.19e6) / 32768, source='profiles/r2_full_summary.txt'),
     'C3_bvp': dict(pipe=31.0, flops=4364., dram=(236.44e6 + 654.39e6) / 32768, source='profiles/r2_full_summary.txt'),
