@@ -408,9 +408,13 @@ def gpu_arm(args):
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu:
-    v, cores, sample, wall = cpu_reference(args.workload, min(M, 65536), args.cpu_steps)
-    cpu = {'value': v, 'unit': 'member-timesteps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
-           'wall_s': round(wall, 2)}
+    try:
+      v, cores, sample, wall = cpu_reference(args.workload, min(M, 65536), args.cpu_steps)
+      cpu = {'value': v, 'unit': 'member-timesteps/s', 'cores': cores, 'kind': 'port', 'sample': sample,
+             'wall_s': round(wall, 2)}
+    except Exception as exc:  # noqa: BLE001 (the GPU numbers above are still worth printing)
+      cpu = {'value': None, 'unit': 'member-timesteps/s', 'cores': os.cpu_count(), 'kind': 'port',
+             'sample': 'failed: %s: %s' % (type(exc).__name__, exc)}
 
   if rank == 0:
     line = {
