@@ -1,6 +1,7 @@
 // Host-buffer entry point (pmoc_model_run_host) and the FP64 roofline probe.
 #include "pmoc_common.cuh"
 
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -47,10 +48,12 @@ struct Mirror {
   // default pool is not touched.
   cudaError_t init() {
     static cudaMemPool_t pools[64] = {};
+    static std::mutex pools_lock;  // (callers on different threads may open their first handle at the same time)
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> guard(pools_lock);
     if (!pools[dev]) {
       cudaMemPoolProps props = {};
       props.allocType = cudaMemAllocationTypePinned;
