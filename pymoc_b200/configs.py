@@ -261,7 +261,7 @@ def c4_jansen_nadeau(M=1, axes=None, sweep=None):
     * kapfac 1.0..1.8 and db -0.004..0: for kapfac <= 0.75 or db >= +0.001 the no-flux bottom condition
       bbot = b[1] drives b[0] - b[1] of a column to within a rounding of zero in steady state, and Psib's
       clip((top-x)/(top-bot)) jumps by the cell's whole transport between a flat and a one-ulp-inverted cell
-      (PMOC_ST_TIE_CELL): 47 % of a kapfac 0.5..2 x db -0.004..+0.002 lattice sat there, 1 % of it missed
+      (PMOC_ST_TIE_CELL): 22 % of a kapfac 0.5..2 x db -0.004..+0.002 lattice carry the bit, 1 % of it missed
       1e-10 because the reference's rounding fell the other way.  On this lattice 2.7 % carry the bit after
       2 401 steps and none misses;
     * tau 0.07..0.2, B 4e3..9e3, KGM 750..950: at weak wind + strong mixing + weak surface flux the
